@@ -1,0 +1,129 @@
+/*
+ * scft_b200.h — C ABI of the B200-native SCFT propagator engine.
+ *
+ * Drop-in boundary for the hot path of giantsda/SCFT: the residual evaluation
+ *      eta (field on interior nodes)  ->  phi_0 - phi   (density mismatch)
+ * i.e. the FEM march of the modified diffusion equation for q(x,s), the density quadrature
+ * and the field updates that call it.  Each entry point cites the reference interface it
+ * replaces (paths relative to the reference repository root).
+ *
+ * Plain C: opaque handle, plain pointers and sizes, int status codes (0 = ok).  The library never
+ * calls exit().  This header does not depend on include order, but like every system header it
+ * must not be included AFTER the reference's nr.h / nrutil.h, which "#define float double"
+ * (nr.h:8) — include it first, or #undef float.
+ *
+ * Index conventions: n = N-2 is the number of INTERIOR nodes; arrays are 0-based
+ * unless the name says nr1 (Numerical-Recipes 1-based, in[1..n]).
+ */
+#ifndef SCFT_B200_H_
+#define SCFT_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define SCFTB_OK 0
+#define SCFTB_ERR_ARG 1        /* bad argument / unsupported size */
+#define SCFTB_ERR_CUDA 2       /* CUDA runtime error (see scftb_last_error) */
+#define SCFTB_ERR_NAN 3        /* NaN in a residual (ADM_chen_C.c:61-66 exit(1)s; we return) */
+#define SCFTB_ERR_NOCONV 4     /* solver hit its iteration limit (adm_chen returns 1) */
+#define SCFTB_ERR_STATE 5      /* call order (e.g. callback without a bound engine) */
+
+/* ---- discretisation of the contour march --------------------------------------------------- */
+#define SCFTB_IE_ROWSCALE 0     /* 1D_FEM.c:95-186 / Matlab_files/simple_FEM_1D_transient.m:34-91 */
+#define SCFTB_IE_CONSISTENT 1   /* deal.II A,B,C (scft.cc:643-656) with an implicit-Euler step    */
+#define SCFTB_IRK4_CONSISTENT 2 /* 2-stage Gauss-Legendre, scft.cc:671-693 + drivescft.cc:130-146 */
+#define SCFTB_QUAD_ROMBERG 0    /* romint.c:21-57 (drivescft.cc:192) */
+#define SCFTB_QUAD_TRAPEZOID 1  /* simple_FEM_1D_transient.m:120-124 */
+
+typedef struct scftb_engine scftb_engine;
+
+/* Replaces the state the reference keeps in SCFT::HeatEquation<2> (SCFT.h:117-155; ctor
+ * scft.cc:22-37: tau, N, total_time_step, L) and the literals of 1D_FEM.c:60-61. */
+typedef struct {
+  int scheme;        /* SCFTB_IE_* / SCFTB_IRK4_* */
+  int N;             /* nodes of the 1D mesh (elements m = N-1) */
+  int nsteps;        /* contour steps n; the reference's total_time_step is n+1 */
+  int quadrature;    /* SCFTB_QUAD_* */
+  double sign;       /* +1: out = phi0 - phi (drivescft.cc:212); -1: phi - phi0 (1D_FEM.c:276) */
+  int max_batch;     /* capacity: number of independent problems held by the engine (>= 1) */
+  int device;        /* CUDA device ordinal */
+  int store_history; /* 1: keep every q(x,s_j) slice of every problem (solution_store,
+                        scft.cc:30); 0: keep only the half the fused quadrature re-reads */
+} scftb_config;
+
+int scftb_create(const scftb_config *cfg, scftb_engine **out);
+int scftb_destroy(scftb_engine *e);
+const char *scftb_last_error(void);
+/* number of kernels launched by the calling thread's engines since the last reset (bench evidence) */
+long scftb_launch_count(int reset);
+
+/* Physical parameters of problem p (all problems when p < 0): surface-layer width tau, film
+ * thickness L and, optionally, N node coordinates (NULL = uniform mesh, drivescft.cc:91-98).
+ * Computes phi_0 = f0_given on the nodes (scft.cc:188-215; 1D_FEM.c:305-319). */
+int scftb_set_problem(scftb_engine *e, int p, double tau, double L, const double *x);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+/* One residual evaluation of problem 0, host buffers.  Replaces
+ * SCFT::HeatEquation<2>::run(double*) (drivescft.cc:81-216) and
+ * simple_FEM_1D_transient(int,double*,double*) (1D_FEM.c:47-287), 0-based. */
+int scftb_residual(scftb_engine *e, const double *eta_mid, double *out);
+/* nprob independent evaluations (parameter sweep, or the n columns of fdjac.c:18-34), host buffers
+ * eta_mid[nprob][N-2], out[nprob][N-2]; H2D and D2H copies are part of the call. */
+int scftb_residual_batch(scftb_engine *e, int nprob, const double *eta_mid, double *out);
+/* Same with DEVICE buffers on a caller stream (cudaStream_t passed as void*); asynchronous. */
+int scftb_residual_batch_device(scftb_engine *e, int nprob, const double *d_eta_mid, double *d_out,
+                                void *stream);
+
+/* Results of the last evaluation of problem p (host buffers). */
+int scftb_get_phi(scftb_engine *e, int p, double *phi /* N */);         /* f0, drivescft.cc:185-193 */
+int scftb_get_Q(scftb_engine *e, int p, double *Q);                      /* (1/L) int q(x,1) dx */
+int scftb_get_f0_given(scftb_engine *e, int p, double *f0 /* N */);     /* scft.cc:188-215 */
+int scftb_get_eta_full(scftb_engine *e, int p, double *eta /* N */);    /* scft.cc:452-490 */
+/* q history, row-major [N][nsteps+1] like solution_store rows 1..N (scft.cc:30,
+ * drivescft.cc:123-152).  Needs store_history = 1. */
+int scftb_get_q_history(scftb_engine *e, int p, double *hist);
+/* Mean-field free energy per segment of the last evaluated field of problem p
+ * (scft.cc:404-450 via print_and_save_yita_1D scft.cc:271-291); f0bar <= 0 computes it the way
+ * testFiBar.cc:19-50 does. */
+int scftb_free_energy(scftb_engine *e, int p, double f0bar, double *F);
+
+/* ---- the reference-shaped residual callback  void f(int n, double* in, double* out) ---------
+ * scftb_bind_global plays the role of the global `heat_equation_solver` (drivescft.cc:50);
+ * scftb_callback_nr1 replaces SCFT_wrapper under #define BROYDN (drivescft.cc:218-243) and
+ * simple_FEM_1D_transient as passed to broydn (1D_FEM.c:356): arrays in[1..n], out[1..n];
+ * scftb_callback_c0 replaces SCFT_wrapper for adm_chen (0-based).  On a CUDA failure they set
+ * scftb_funcerr (the analogue of broydn.c:25 funcerr) instead of aborting. */
+int scftb_bind_global(scftb_engine *e);
+void scftb_callback_nr1(int n, double *in, double *out);
+void scftb_callback_c0(int n, double *in, double *out);
+/* fixed-point image x + (phi0 - phi) for adm (comment at drivescft.cc:212), 0-based */
+void scftb_callback_fixedpoint_c0(int n, double *in, double *out);
+extern int scftb_funcerr;
+
+/* ---- field updates -------------------------------------------------------------------------- */
+typedef void (*scftb_func)(int n, double *in, double *out);
+
+/* Host-flow solvers with the reference argument lists (generic callback, one problem). */
+/* adm_chen (NR_chen.h:30-34, ADM_chen_C.c:18-147); returns 0 converged / 1 not / SCFTB_ERR_NAN */
+int scftb_adm_chen(scftb_func f, double *x_old, double tol, int maxIteration, int n, double lmd,
+                   int nn, int Final);
+/* adm (adm.c:24-313) for x = f(x); 0-based (flag 0); *check 0 converged / 1 failed */
+int scftb_adm(scftb_func f, double *x, int n, int *check, int maxits);
+/* broydn (broydn.c:44-292), x 0-based here; tolf in / achieved max|f| out via *err; jc as in
+ * broydn.c:26-27.  When f == scftb_callback_c0 the finite-difference Jacobian (fdjac.c:18-34)
+ * is evaluated as ONE batch of n residuals on the device. */
+int scftb_broydn(scftb_func f, double *x, int n, int *check, double *err, int *jc);
+
+/* Device-resident batched Anderson mixing (adm_chen semantics) on the engine's problems:
+ * x[nprob][N-2] host in/out.  All nprob problems iterate in lock-step, each with its own
+ * history, Gram matrix, gaussj solve and relaxation; nothing but the per-problem error norms
+ * leaves the device between iterations.  iters_out/err_out (may be NULL): per problem. */
+int scftb_adm_chen_batch(scftb_engine *e, int nprob, double *x, double tol, int maxIteration,
+                         double lmd, int nn, int Final, int *iters_out, double *err_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCFT_B200_H_ */

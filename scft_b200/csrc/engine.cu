@@ -1,0 +1,439 @@
+// engine.cu — C-ABI implementation of the SCFT propagator engine (see include/scft_b200.h).
+// Host side: owns the device buffers of up to max_batch independent problems, computes the
+// per-mesh constants (phi_0, quadrature weights) once, and launches the march kernel.
+#include "engine.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "march1d.cuh"
+
+namespace scftb {
+
+thread_local std::string g_last_error;
+std::atomic<long> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(SCFTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));             \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Romberg quadrature as a weight vector.  romint.c:21-57 builds trapezoid sums on 1,2,4,...,m
+// intervals and extrapolates the last K=5 of them to h^2 -> 0 with Neville's scheme
+// (polint.c:5-42).  Both are linear in f, so the result is sum_j w_j f_j with
+// w = sum_k lagrange_k(0) * (trapezoid weights of level k), h_k = 4^-k.
+// ---------------------------------------------------------------------------------------------
+int romberg_weights(int m, double hh, std::vector<double> &w) {
+  int levels = 0;
+  while ((1 << levels) < m) levels++;
+  if ((1 << levels) != m || levels < 4) return 1;  // romint.c:29-33 needs m = 2^k >= 16
+  const int K = 5, M = levels + 1;                 // trapezoid levels 1..M, level l has 2^(l-1) intervals
+  double hk[K], ck[K];
+  for (int k = 0; k < K; k++) hk[k] = std::pow(0.25, (double)(M - K + k));  // h[l] = 4^-(l-1)
+  for (int k = 0; k < K; k++) {  // Lagrange basis at 0
+    double c = 1.0;
+    for (int j = 0; j < K; j++)
+      if (j != k) c *= (0.0 - hk[j]) / (hk[k] - hk[j]);
+    ck[k] = c;
+  }
+  w.assign(m + 1, 0.0);
+  for (int k = 0; k < K; k++) {
+    int level = M - K + 1 + k;
+    int stride = m >> (level - 1);
+    double hl = hh * stride;
+    for (int i = 0; i <= m; i += stride) w[i] += ck[k] * hl * ((i == 0 || i == m) ? 0.5 : 1.0);
+  }
+  return 0;
+}
+
+void trapezoid_weights(int m, double hh, std::vector<double> &w) {  // simple_FEM_1D_transient.m:120-124
+  w.assign(m + 1, hh);
+  w[0] = w[m] = 0.5 * hh;
+}
+
+// phi_0 on the nodes (scft.cc:188-215): ((e^u-1)/(e^u+1))^2, u = 4 tau x/(tau^2-x^2), x <= tau,
+// mirrored about the film centre, NaN -> 1.
+static double f0_point(double x, double tau) {
+  double e = std::exp(4 * tau * x / (tau * tau - x * x));
+  double v = std::pow(e - 1, 2) / std::pow(e + 1, 2);
+  return std::isnan(v) ? 1.0 : v;
+}
+void f0_given(int N, const double *x, double tau, double *f0) {
+  for (int i = 0; i < N; i++) f0[i] = 1.0;
+  for (int i = 0; i < N; i++) {
+    if (x[i] <= tau) {
+      f0[i] = f0_point(x[i], tau);
+      f0[N - i - 1] = f0[i];
+    } else
+      break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// natural-spline wall values on a NON-uniform mesh (scft.cc:452-490, spline_chen.c:12-106 with
+// m = 0): the reference solves the tridiagonal system densely with gaussj; here one thread per
+// problem runs Thomas over the N-2 knots.  Uniform meshes never need this (see eta_node()).
+// ---------------------------------------------------------------------------------------------
+__global__ void spline_bnd_kernel(int nprob, int N, const double *x, const double *eta_mid, double *scratch,
+                                  double *eta_bnd) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nprob) return;
+  const int Nx = N - 2;
+  const double *xk = x + (size_t)p * N + 1;  // knots = interior nodes
+  const double *y = eta_mid + (size_t)p * Nx;
+  double *cp = scratch + (size_t)p * 2 * Nx, *dp = cp + Nx;
+  // rows i=1..Nx-2: (x_i-x_{i-1})/6, (x_{i+1}-x_{i-1})/3, (x_{i+1}-x_i)/6 ; rows 0, Nx-1: M = 0
+  cp[0] = 0.0; dp[0] = 0.0;
+  for (int i = 1; i < Nx - 1; i++) {
+    double lo = (xk[i] - xk[i - 1]) / 6., di = (xk[i + 1] - xk[i - 1]) / 3., up = (xk[i + 1] - xk[i]) / 6.;
+    double rhs = (y[i + 1] - y[i]) / (xk[i + 1] - xk[i]) - (y[i] - y[i - 1]) / (xk[i] - xk[i - 1]);
+    double den = di - lo * cp[i - 1];
+    cp[i] = up / den;
+    dp[i] = (rhs - lo * dp[i - 1]) / den;
+  }
+  double Mn = 0.0, M1 = 0.0, Mlast1 = 0.0;
+  for (int i = Nx - 2; i >= 1; i--) {
+    Mn = dp[i] - cp[i] * Mn;
+    if (i == Nx - 2) Mlast1 = Mn;
+    if (i == 1) M1 = Mn;
+  }
+  const double *xf = x + (size_t)p * N;
+  {  // left wall: klo=0, khi=1
+    double h = xk[1] - xk[0], a = (xk[1] - xf[0]) / h, b = (xf[0] - xk[0]) / h;
+    eta_bnd[2 * p] = a * y[0] + b * y[1] + ((a * a * a - a) * 0.0 + (b * b * b - b) * M1) * (h * h) / 6.0;
+  }
+  {  // right wall: klo=Nx-2, khi=Nx-1
+    double h = xk[Nx - 1] - xk[Nx - 2], a = (xk[Nx - 1] - xf[N - 1]) / h, b = (xf[N - 1] - xk[Nx - 2]) / h;
+    eta_bnd[2 * p + 1] =
+        a * y[Nx - 2] + b * y[Nx - 1] + ((a * a * a - a) * Mlast1 + (b * b * b - b) * 0.0) * (h * h) / 6.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef void (*march_fn)(MarchParams);
+struct KernelChoice {
+  int C, T;
+  march_fn fn;
+};
+
+template <int C, int TMAX, int MINB>
+static march_fn pick(bool uni) {
+  return uni ? (march_fn)march_ie_kernel<C, true, TMAX, MINB> : (march_fn)march_ie_kernel<C, false, TMAX, MINB>;
+}
+
+// nodes per thread C and threads per problem T for ni interior nodes
+static int choose_kernel(int ni, bool uni, KernelChoice &kc) {
+  int C = 1;
+  while (C < 16 && (ni + C - 1) / C > 128) C *= 2;
+  int T = ((ni + C - 1) / C + 31) / 32 * 32;
+  int tmax = 128;
+  switch (C) {
+    case 1: kc.fn = pick<1, 128, 4>(uni); break;
+    case 2: kc.fn = pick<2, 128, 4>(uni); break;
+    case 4: kc.fn = pick<4, 128, 4>(uni); break;
+    case 8: kc.fn = pick<8, 128, 3>(uni); break;
+    default:
+      if (T <= 128) kc.fn = pick<16, 128, 1>(uni);
+      else { kc.fn = pick<16, 256, 1>(uni); tmax = 256; }
+      break;
+  }
+  if (T > tmax) return 1;
+  kc.C = C; kc.T = T;
+  return 0;
+}
+
+}  // namespace scftb
+
+using namespace scftb;
+
+struct scftb_engine {
+  scftb_config cfg;
+  int ni;
+  bool uniform;
+  KernelChoice kc;
+  int slots;       // resident CTAs
+  int nslices;     // history slices per problem/slot
+  size_t SL;       // doubles per slice
+  cudaStream_t stream;
+  // host mirrors
+  std::vector<double> h_tau, h_L, h_x, h_f0, h_w;
+  bool params_dirty;
+  int last_nprob;
+  // device buffers
+  double *d_eta, *d_out, *d_phi, *d_Q, *d_f0, *d_L, *d_x, *d_eta_bnd, *d_w, *d_hist, *d_eta_full, *d_scratch;
+};
+
+static int upload_params(scftb_engine *e) {
+  if (!e->params_dirty) return SCFTB_OK;
+  const int N = e->cfg.N, B = e->cfg.max_batch;
+  CK(cudaMemcpyAsync(e->d_f0, e->h_f0.data(), sizeof(double) * N * B, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->d_L, e->h_L.data(), sizeof(double) * B, cudaMemcpyHostToDevice, e->stream));
+  if (!e->uniform) {
+    if (!e->d_x) {
+      CK(cudaMalloc(&e->d_x, sizeof(double) * N * B));
+      CK(cudaMalloc(&e->d_eta_bnd, sizeof(double) * 2 * B));
+      CK(cudaMalloc(&e->d_scratch, sizeof(double) * 2 * e->ni * B));
+    }
+    CK(cudaMemcpyAsync(e->d_x, e->h_x.data(), sizeof(double) * N * B, cudaMemcpyHostToDevice, e->stream));
+  }
+  e->params_dirty = false;
+  return SCFTB_OK;
+}
+
+extern "C" {
+
+const char *scftb_last_error(void) { return g_last_error.c_str(); }
+
+long scftb_launch_count(int reset) {
+  long v = g_launches.load();
+  if (reset) g_launches.store(0);
+  return v;
+}
+
+int scftb_create(const scftb_config *cfg, scftb_engine **out) {
+  if (!cfg || !out) return fail(SCFTB_ERR_ARG, "null argument");
+  if (cfg->N < 4 || cfg->nsteps < 2 || cfg->max_batch < 1) return fail(SCFTB_ERR_ARG, "N>=4, nsteps>=2, max_batch>=1");
+  if (cfg->scheme != SCFTB_IE_ROWSCALE && cfg->scheme != SCFTB_IE_CONSISTENT)
+    return fail(SCFTB_ERR_ARG, "scheme not supported by this build");
+  scftb_engine *e = new scftb_engine();
+  e->cfg = *cfg;
+  e->ni = cfg->N - 2;
+  e->uniform = true;
+  e->params_dirty = true;
+  e->last_nprob = 0;
+  e->d_x = e->d_eta_bnd = e->d_scratch = nullptr;
+  const int N = cfg->N, B = cfg->max_batch, n = cfg->nsteps;
+  if (cfg->quadrature == SCFTB_QUAD_ROMBERG) {
+    if (romberg_weights(n, 1.0 / n, e->h_w)) {
+      delete e;
+      return fail(SCFTB_ERR_ARG, "Romberg quadrature needs nsteps = 2^k >= 16 (romint.c:28-33)");
+    }
+  } else
+    trapezoid_weights(n, 1.0 / n, e->h_w);
+  if (choose_kernel(e->ni, true, e->kc)) {
+    delete e;
+    return fail(SCFTB_ERR_ARG, "N too large for the register-resident march (N <= 4098 in this build)");
+  }
+#define CKD(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      int rc = fail(SCFTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));           \
+      delete e;                                                                                    \
+      return rc;                                                                                   \
+    }                                                                                              \
+  } while (0)
+  CKD(cudaSetDevice(cfg->device));
+  CKD(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->SL = (size_t)e->kc.T * e->kc.C;
+  int sms = 0, occ = 0;
+  CKD(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  size_t smem = sizeof(double) * SmemLayout::doubles(e->kc.T);
+  for (int uni = 0; uni < 2; uni++) {
+    KernelChoice k2;
+    choose_kernel(e->ni, uni, k2);
+    CKD(cudaFuncSetAttribute((const void *)k2.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)e->kc.fn, e->kc.T, smem));
+  if (occ < 1) occ = 1;
+  e->slots = std::min(B, sms * occ);
+  e->nslices = cfg->store_history ? n + 1 : n / 2 + 1;
+  size_t nh = (size_t)(cfg->store_history ? B : e->slots) * e->nslices * e->SL;
+  e->h_tau.assign(B, 0.0);
+  e->h_L.assign(B, 1.0);
+  e->h_f0.assign((size_t)N * B, 1.0);
+  CKD(cudaMalloc(&e->d_eta, sizeof(double) * e->ni * B));
+  CKD(cudaMalloc(&e->d_out, sizeof(double) * e->ni * B));
+  CKD(cudaMalloc(&e->d_phi, sizeof(double) * N * B));
+  CKD(cudaMalloc(&e->d_eta_full, sizeof(double) * N * B));
+  CKD(cudaMalloc(&e->d_Q, sizeof(double) * B));
+  CKD(cudaMalloc(&e->d_f0, sizeof(double) * N * B));
+  CKD(cudaMalloc(&e->d_L, sizeof(double) * B));
+  CKD(cudaMalloc(&e->d_w, sizeof(double) * (n + 1)));
+  CKD(cudaMalloc(&e->d_hist, sizeof(double) * nh));
+  CKD(cudaMemcpy(e->d_w, e->h_w.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice));
+  *out = e;
+  return SCFTB_OK;
+}
+
+int scftb_engine_max_batch(scftb_engine *e) { return e ? e->cfg.max_batch : 0; }
+
+int scftb_destroy(scftb_engine *e) {
+  if (!e) return SCFTB_OK;
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->stream);
+  for (double *p : {e->d_eta, e->d_out, e->d_phi, e->d_Q, e->d_f0, e->d_L, e->d_x, e->d_eta_bnd, e->d_w, e->d_hist,
+                    e->d_eta_full, e->d_scratch})
+    if (p) cudaFree(p);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return SCFTB_OK;
+}
+
+int scftb_set_problem(scftb_engine *e, int p, double tau, double L, const double *x) {
+  if (!e || p >= e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "bad problem index");
+  const int N = e->cfg.N, B = e->cfg.max_batch;
+  if (x && e->uniform) {  // switch the engine to explicit node coordinates
+    e->h_x.assign((size_t)N * B, 0.0);
+    for (int q = 0; q < B; q++)
+      for (int i = 0; i < N; i++) e->h_x[(size_t)q * N + i] = e->h_L[q] * i / (N - 1);
+    e->uniform = false;
+    if (choose_kernel(e->ni, false, e->kc)) return fail(SCFTB_ERR_ARG, "N too large");
+  }
+  std::vector<double> xs(N);
+  for (int q = (p < 0 ? 0 : p); q < (p < 0 ? B : p + 1); q++) {
+    e->h_tau[q] = tau;
+    e->h_L[q] = L;
+    for (int i = 0; i < N; i++) xs[i] = x ? x[i] : L * i / (N - 1);  // subdivided_hyper_rectangle, drivescft.cc:94-98
+    if (!e->uniform) std::copy(xs.begin(), xs.end(), e->h_x.begin() + (size_t)q * N);
+    f0_given(N, xs.data(), tau, &e->h_f0[(size_t)q * N]);
+  }
+  e->params_dirty = true;
+  return SCFTB_OK;
+}
+
+static int launch_march(scftb_engine *e, int nprob, const double *d_eta, double *d_out, cudaStream_t st) {
+  MarchParams P;
+  P.N = e->cfg.N; P.ni = e->ni; P.nsteps = e->cfg.nsteps;
+  P.scheme = e->cfg.scheme; P.nprob = nprob; P.store_full = e->cfg.store_history;
+  P.uniform = e->uniform ? 1 : 0; P.sign = e->cfg.sign;
+  P.eta_mid = d_eta; P.f0 = e->d_f0; P.L = e->d_L; P.x = e->d_x; P.eta_bnd = e->d_eta_bnd; P.w = e->d_w;
+  P.hist = e->d_hist; P.hist_stride = (long long)e->nslices * (long long)e->SL;
+  P.out = d_out; P.phi = e->d_phi; P.Q = e->d_Q; P.eta_full = e->d_eta_full;
+  if (!e->uniform) {
+    spline_bnd_kernel<<<(nprob + 63) / 64, 64, 0, st>>>(nprob, P.N, e->d_x, d_eta, e->d_scratch, e->d_eta_bnd);
+    g_launches++;
+  }
+  int grid = std::min(nprob, e->slots);
+  size_t smem = sizeof(double) * SmemLayout::doubles(e->kc.T);
+  e->kc.fn<<<grid, e->kc.T, smem, st>>>(P);
+  g_launches++;
+  CK(cudaGetLastError());
+  e->last_nprob = nprob;
+  return SCFTB_OK;
+}
+
+int scftb_residual_batch_device(scftb_engine *e, int nprob, const double *d_eta_mid, double *d_out, void *stream) {
+  if (!e || nprob < 1 || nprob > e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "nprob out of range");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (e->params_dirty) {
+    int rc = upload_params(e);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return launch_march(e, nprob, d_eta_mid, d_out, st);
+}
+
+int scftb_residual_batch(scftb_engine *e, int nprob, const double *eta_mid, double *out) {
+  if (!e || nprob < 1 || nprob > e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "nprob out of range");
+  CK(cudaSetDevice(e->cfg.device));
+  int rc = upload_params(e);
+  if (rc) return rc;
+  const size_t bytes = sizeof(double) * (size_t)e->ni * nprob;
+  CK(cudaMemcpyAsync(e->d_eta, eta_mid, bytes, cudaMemcpyHostToDevice, e->stream));
+  rc = launch_march(e, nprob, e->d_eta, e->d_out, e->stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return SCFTB_OK;
+}
+
+int scftb_residual(scftb_engine *e, const double *eta_mid, double *out) { return scftb_residual_batch(e, 1, eta_mid, out); }
+
+static int fetch(scftb_engine *e, const double *d, size_t off, size_t cnt, double *h) {
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(h, d + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+  return SCFTB_OK;
+}
+
+int scftb_get_phi(scftb_engine *e, int p, double *phi) {
+  if (!e || p < 0 || p >= e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "bad problem index");
+  return fetch(e, e->d_phi, (size_t)p * e->cfg.N, e->cfg.N, phi);
+}
+int scftb_get_Q(scftb_engine *e, int p, double *Q) {
+  if (!e || p < 0 || p >= e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "bad problem index");
+  return fetch(e, e->d_Q, p, 1, Q);
+}
+int scftb_get_eta_full(scftb_engine *e, int p, double *eta) {
+  if (!e || p < 0 || p >= e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "bad problem index");
+  return fetch(e, e->d_eta_full, (size_t)p * e->cfg.N, e->cfg.N, eta);
+}
+int scftb_get_f0_given(scftb_engine *e, int p, double *f0) {
+  if (!e || p < 0 || p >= e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "bad problem index");
+  std::copy(e->h_f0.begin() + (size_t)p * e->cfg.N, e->h_f0.begin() + (size_t)(p + 1) * e->cfg.N, f0);
+  return SCFTB_OK;
+}
+
+int scftb_get_q_history(scftb_engine *e, int p, double *hist) {
+  if (!e || p < 0 || p >= e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "bad problem index");
+  if (!e->cfg.store_history) return fail(SCFTB_ERR_STATE, "engine created with store_history = 0");
+  const int N = e->cfg.N, n = e->cfg.nsteps, T = e->kc.T, C = e->kc.C;
+  std::vector<double> raw((size_t)e->nslices * e->SL);
+  int rc = fetch(e, e->d_hist, (size_t)p * e->nslices * e->SL, raw.size(), raw.data());
+  if (rc) return rc;
+  std::fill(hist, hist + (size_t)N * (n + 1), 0.0);
+  for (int j = 0; j <= n; j++)
+    for (int g = 0; g < e->ni; g++) {
+      int t = g / C, k = g % C;
+      hist[(size_t)(g + 1) * (n + 1) + j] = raw[(size_t)j * e->SL + (size_t)k * T + t];
+    }
+  return SCFTB_OK;
+}
+
+int scftb_free_energy(scftb_engine *e, int p, double f0bar, double *F) {
+  if (!e || p < 0 || p >= e->cfg.max_batch || !F) return fail(SCFTB_ERR_ARG, "bad argument");
+  const int N = e->cfg.N;
+  std::vector<double> eta(N), xs(N);
+  int rc = scftb_get_eta_full(e, p, eta.data());
+  if (rc) return rc;
+  const double L = e->h_L[p], tau = e->h_tau[p];
+  for (int i = 0; i < N; i++) xs[i] = e->uniform ? L * i / (N - 1) : e->h_x[(size_t)p * N + i];
+  std::vector<double> w;
+  if (f0bar <= 0) {  // testFiBar.cc:19-50
+    const int M = (1 << 16) + 1;
+    std::vector<double> xx(M), ff(M);
+    for (int i = 0; i < M; i++) xx[i] = L / (M - 1) * i;
+    f0_given(M, xx.data(), tau, ff.data());
+    romberg_weights(M - 1, L / (M - 1), w);
+    double s = 0;
+    for (int i = 0; i < M; i++) s += w[i] * ff[i];
+    f0bar = s / L;
+  }
+  const int nplot = (1 << 18) + 1;  // scft.cc:271
+  std::vector<double> xp(nplot), f0(nplot);
+  for (int i = 0; i < nplot; i++) xp[i] = L * i / (nplot - 1);
+  f0_given(nplot, xp.data(), tau, f0.data());
+  romberg_weights(nplot - 1, L / (nplot - 1), w);
+  double I = 0;
+  int k = 0;
+  for (int i = 0; i < nplot; i++) {  // piecewise-linear eta_h (FEFieldFunction on Q1, scft.cc:280-281)
+    while (k < N - 2 && xp[i] > xs[k + 1]) k++;
+    double t = (xp[i] - xs[k]) / (xs[k + 1] - xs[k]);
+    I += w[i] * ((1 - t) * eta[k] + t * eta[k + 1]) * f0[i];
+  }
+  *F = (I / f0bar / L + std::log(f0bar)) / (-1000.);  // scft.cc:446-447
+  return SCFTB_OK;
+}
+
+int scftb_adm_chen_batch(scftb_engine *e, int nprob, double *x, double tol, int maxIteration, double lmd, int nn,
+                         int Final, int *iters_out, double *err_out) {
+  (void)e; (void)nprob; (void)x; (void)tol; (void)maxIteration; (void)lmd; (void)nn; (void)Final; (void)iters_out; (void)err_out;
+  return fail(SCFTB_ERR_STATE, "scftb_adm_chen_batch: not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,401 @@
+// march1d.cuh — the contour-march kernel of the 1D SCFT residual (sm_100a, fp64).
+//
+// One CTA per problem.  The whole evaluation
+//     assemble (M + ds*K + ds*M_w)  ->  factor once  ->  n implicit-Euler steps  ->
+//     phi(x) = int q(x,s) q(x,1-s) ds  ->  residual, Q
+// runs inside one launch; q, the factor and the phi accumulators never leave the register file.
+// It replaces, for the tridiagonal (1D / y-invariant strip) case, the reference's
+//     assembly         1D_FEM.c:95-186, scft.cc:589-669
+//     factorisation    KSPSetUp/PCICC 1D_FEM.c:191-206, UMFPACK scft.cc:695
+//     contour loop     1D_FEM.c:208-228, drivescft.cc:130-165
+//     quadrature       1D_FEM.c:260-277, drivescft.cc:184-213 (romint.c:21-57 as a weight vector)
+//
+// Parallel-in-x solve of the constant tridiagonal system (nested substructuring):
+//   level 1  each thread owns C consecutive nodes: C-1 chunk-interior nodes + 1 separator.
+//            Thomas on the chunk (pivots pre-inverted, rows pre-scaled), two precomputed spikes.
+//   level 2  the 31 separators inside a warp: cyclic reduction in warp shuffles with
+//            precomputed multipliers (5 stages), two precomputed warp spikes.
+//   level 3  the warp separators (blockDim/32 unknowns): precomputed dense inverse, one
+//            shared-memory exchange and ONE __syncthreads per contour step.
+// All elimination coefficients are computed once per field update and reused for all n steps.
+//
+// History layout in HBM: slice j of a problem is T*C doubles, element (k,t) at k*T+t, so a warp
+// stores/loads 256 contiguous bytes per instruction.  Only slices j < n/2 are re-read: Romberg
+// weights are symmetric, so phi_i = sum_{j>n/2} 2 w_j q_i(j) q_i(n-j) + w_{n/2} q_i(n/2)^2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace scftb {
+
+struct MarchParams {
+  int N;                  // nodes
+  int ni;                 // interior nodes N-2
+  int nsteps;             // contour steps n
+  int scheme;             // 0 row-scaled C, 1 consistent C
+  int nprob;              // problems in this launch
+  int store_full;         // 1: store every slice, per problem; 0: half history, per CTA slot
+  int uniform;            // 1: uniform mesh (x == nullptr)
+  double sign;
+  const double *eta_mid;  // [nprob][ni]
+  const double *f0;       // [nprob][N]
+  const double *L;        // [nprob]
+  const double *x;        // [nprob][N] node coordinates (non-uniform) or nullptr
+  const double *eta_bnd;  // [nprob][2] spline-extrapolated wall values (non-uniform) or nullptr
+  const double *w;        // [nsteps+1] quadrature weights
+  double *hist;           // history slices
+  long long hist_stride;  // doubles per problem (store_full) or per CTA slot
+  double *out;            // [nprob][ni]  sign*(phi0 - phi)
+  double *phi;            // [nprob][N]
+  double *Q;              // [nprob]
+  double *eta_full;       // [nprob][N] (diagnostic, scft.cc:452-490) or nullptr
+};
+
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_dn_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_d(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+
+// eta on node i (0..N-1).  Wall nodes: natural-spline extrapolation of the interior values
+// (scft.cc:456-475 -> spline_chen.c:77-100).  With y''=0 at the end knots the cubic term of the
+// first/last piece vanishes on a uniform mesh, leaving the linear extrapolation a*y0+b*y1.
+__device__ __forceinline__ double eta_node(const MarchParams &P, int p, int i, double L) {
+  const double *em = P.eta_mid + (size_t)p * P.ni;
+  if (i >= 1 && i <= P.N - 2) return em[i - 1];
+  if (!P.uniform) return P.eta_bnd[2 * p + (i == 0 ? 0 : 1)];
+  const int N = P.N;
+  if (i == 0) {
+    double x0 = L * 0 / (N - 1), x1 = L * 1 / (N - 1), x2 = L * 2 / (N - 1);
+    double h = x2 - x1, a = (x2 - x0) / h, b = (x0 - x1) / h;
+    return a * em[0] + b * em[1];
+  }
+  double xe = L * (N - 1) / (N - 1), xa = L * (N - 3) / (N - 1), xb = L * (N - 2) / (N - 1);
+  double h = xb - xa, a = (xb - xe) / h, b = (xe - xa) / h;
+  return a * em[P.ni - 2] + b * em[P.ni - 1];
+}
+
+struct Row { double Al, Ad, Au, Tl, Td, Tu; };
+
+// Row g (0-based interior index) of A (mass) and T = A + ds*(B + C).
+__device__ __forceinline__ Row assemble_row(const MarchParams &P, int p, int g, double L, double dt) {
+  Row r;
+  if (g >= P.ni) { r.Al = r.Ad = r.Au = 0.0; r.Tl = r.Tu = 0.0; r.Td = 1.0; return r; }  // padding
+  const int i = g + 1;
+  double a1, a2, bl, bd, bu;
+  if (P.uniform) {  // 1D_FEM.c:61,95-98
+    double h = L / (P.N - 1);
+    a1 = a2 = h;
+    r.Al = h / 6; r.Ad = 2. / 3 * h; r.Au = h / 6;
+    bl = -1 / h; bd = 2. / h; bu = -1 / h;
+  } else {          // simple_FEM_1D_transient.m:35-57
+    const double *x = P.x + (size_t)p * P.N;
+    a1 = x[i] - x[i - 1]; a2 = x[i + 1] - x[i];
+    r.Al = a1 / 6; r.Ad = a1 / 3 + a2 / 3; r.Au = a2 / 6;
+    bl = -1 / a1; bd = 1 / a1 + 1 / a2; bu = -1 / a2;
+  }
+  double e0 = eta_node(P, p, i, L), cl, cd, cu;
+  if (P.scheme == 0) {  // row-scaled lumping, 1D_FEM.c:104-105
+    cl = r.Al * e0; cd = r.Ad * e0; cu = r.Au * e0;
+  } else {              // (eta_h phi_i, phi_j), 2-point Gauss exact for linear eta_h (scft.cc:653-655)
+    double em = eta_node(P, p, i - 1, L), ep = eta_node(P, p, i + 1, L);
+    cl = a1 * (em + e0) / 12;
+    cu = a2 * (e0 + ep) / 12;
+    cd = a1 * (em + 3 * e0) / 12 + a2 * (3 * e0 + ep) / 12;
+  }
+  r.Tl = r.Al + dt * (bl + cl);
+  r.Td = r.Ad + dt * (bd + cd);
+  r.Tu = r.Au + dt * (bu + cu);
+  if (g == 0) { r.Al = 0.0; r.Tl = 0.0; }            // q(0,s) = 0   (1D_FEM.c:179-180,213)
+  if (g == P.ni - 1) { r.Au = 0.0; r.Tu = 0.0; }     // q(L,s) = 0   (1D_FEM.c:181-182,214)
+  return r;
+}
+
+// shared-memory carve-up (doubles)
+struct SmemLayout {
+  int T, nw;
+  __host__ __device__ static int doubles(int T) {
+    int nw = T / 32;
+    return 2 * T            // setup exchange gl0 / gr0
+           + 9 * nw         // level-3 coefficients
+           + nw * nw        // Minv
+           + 2 * nw * 8     // per-step publish buffers (double-buffered)
+           + nw + 8;        // reduction scratch
+  }
+};
+
+constexpr int PUB = 8;  // doubles per warp in a publish buffer
+
+template <int C, bool UNI, int TMAX, int MINB>
+__global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
+  constexpr int CI = C - 1;             // chunk-interior nodes per thread
+  constexpr int CA = CI > 0 ? CI : 1;   // array extent
+  const int t = threadIdx.x, T = blockDim.x, lane = t & 31, wid = t >> 5, nw = T >> 5;
+  extern __shared__ double sm[];
+  double *ex0 = sm, *ex1 = sm + T;
+  double *l3 = sm + 2 * T;              // [9][nw]: P D Nx GL0 GR0 GL30 GR30 cAu csu
+  double *Minv = l3 + 9 * nw;           // [nw][nw]
+  double *pub = Minv + nw * nw;         // [2][nw][PUB]
+  double *red = pub + 2 * nw * PUB;     // [nw + 8]
+  const int n = P.nsteps;
+  const double dt = 1.0 / n;            // time_step = 1/(total_time_step-1), scft.cc:29
+  const int SL = T * C;                 // doubles per history slice
+
+  for (int p = blockIdx.x; p < P.nprob; p += gridDim.x) {
+    const double L = P.L[p];
+    // ------------------------------------------------------------------ assembly + level 1
+    double ca[CA], cd[CA], cu[CA];      // pre-scaled rows of A on chunk-interior nodes (UNI: ca==cu)
+    double al[CA], be[CA], gl[CA], gr[CA];
+    double sAl, sAd, sAu, sl, sd, su;   // separator row of A and T
+    {
+      Row rs = assemble_row(P, p, t * C + CI, L, dt);
+      sAl = rs.Al; sAd = rs.Ad; sAu = rs.Au; sl = rs.Tl; sd = rs.Td; su = rs.Tu;
+    }
+    if constexpr (CI > 0) {
+      double Tl0 = 0, TuL = 0, pinv_prev = 0, Tu_prev = 0;
+#pragma unroll
+      for (int k = 0; k < CI; k++) {
+        Row r = assemble_row(P, p, t * C + k, L, dt);
+        double piv = (k == 0) ? r.Td : r.Td - (r.Tl * pinv_prev) * Tu_prev;
+        double pinv = 1.0 / piv;
+        // UNI: one off-diagonal coefficient serves both neighbours; the Dirichlet zeroing of A is
+        // then carried by the neighbour values themselves (wall / padding nodes are exactly 0).
+        ca[k] = pinv * ((UNI && r.Al == 0.0) ? r.Au : r.Al); cd[k] = pinv * r.Ad; cu[k] = pinv * r.Au;
+        al[k] = (k == 0) ? 0.0 : pinv * r.Tl;
+        be[k] = (k == CI - 1) ? 0.0 : pinv * r.Tu;
+        if (k == 0) Tl0 = pinv * r.Tl;          // scaled coupling to the left separator
+        if (k == CI - 1) TuL = pinv * r.Tu;     // scaled coupling to the own (right) separator
+        pinv_prev = pinv; Tu_prev = r.Tu;
+      }
+      // spikes gl = T_loc^-1 (Tl_first e_first), gr = T_loc^-1 (Tu_last e_last)
+      double y[CA];
+      y[0] = Tl0;
+#pragma unroll
+      for (int k = 1; k < CI; k++) y[k] = -al[k] * y[k - 1];
+      gl[CI - 1] = y[CI - 1];
+#pragma unroll
+      for (int k = CI - 2; k >= 0; k--) gl[k] = y[k] - be[k] * gl[k + 1];
+      gr[CI - 1] = TuL;
+#pragma unroll
+      for (int k = CI - 2; k >= 0; k--) gr[k] = -be[k] * gr[k + 1];
+    }
+    // ------------------------------------------------------------------ Schur rows on separators
+    double a, b, c;
+    __syncthreads();  // previous problem's readers of sm are done
+    if constexpr (CI > 0) {
+      ex0[t] = gl[0]; ex1[t] = gr[0];
+      __syncthreads();
+      double gl0n = (t + 1 < T) ? ex0[t + 1] : 0.0, gr0n = (t + 1 < T) ? ex1[t + 1] : 0.0;
+      a = -sl * gl[CI - 1];
+      b = sd - sl * gr[CI - 1] - su * gl0n;
+      c = -su * gr0n;
+    } else {
+      a = sl; b = sd; c = su;
+    }
+    // ------------------------------------------------------------------ level 2: warp PCR setup
+    double l3P = a, l3D = b, l3N = c;       // lane 31: row of the warp separator
+    double A0 = (lane == 0) ? a : 0.0, C30 = (lane == 30) ? c : 0.0;
+    if (lane == 31) { a = 0.0; b = 1.0; c = 0.0; }
+    if (lane == 0) a = 0.0;
+    if (lane == 30) c = 0.0;
+    double pa_[5], pg_[5];
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+      const int d = 1 << s;
+      double am = shfl_up_d(a, d), bm = shfl_up_d(b, d), cm = shfl_up_d(c, d);
+      double ap = shfl_dn_d(a, d), bp = shfl_dn_d(b, d), cp = shfl_dn_d(c, d);
+      double alpha = (lane >= d) ? -a / bm : 0.0;
+      double gamma = (lane + d <= 31) ? -c / bp : 0.0;
+      if (lane < d) { am = 0.0; cm = 0.0; }
+      if (lane + d > 31) { ap = 0.0; cp = 0.0; }
+      b = b + alpha * cm + gamma * ap;
+      a = alpha * am;
+      c = gamma * cp;
+      pa_[s] = alpha; pg_[s] = gamma;
+    }
+    const double binv = 1.0 / b;
+    auto pcr = [&](double r) {
+#pragma unroll
+      for (int s = 0; s < 5; s++) {
+        const int d = 1 << s;
+        double rm = shfl_up_d(r, d), rp = shfl_dn_d(r, d);
+        r = r + pa_[s] * rm + pg_[s] * rp;
+      }
+      return r * binv;
+    };
+    const double GL = pcr(A0), GR = pcr(C30);
+    // ------------------------------------------------------------------ level 3 setup
+    if (lane == 31) { l3[0 * nw + wid] = l3P; l3[1 * nw + wid] = l3D; l3[2 * nw + wid] = l3N;
+                      l3[7 * nw + wid] = sAu; l3[8 * nw + wid] = (CI > 0) ? su : 0.0; }
+    if (lane == 0) { l3[3 * nw + wid] = GL; l3[4 * nw + wid] = GR; }
+    if (lane == 30) { l3[5 * nw + wid] = GL; l3[6 * nw + wid] = GR; }
+    __syncthreads();
+    if (t < nw) {  // thread v: column v of M^-1 by Thomas (M is tridiagonal, diagonally dominant)
+      double *col = ex0;  // scratch [nw][nw] needs nw*nw <= 2T doubles: nw <= 64 ok
+      double *cp_ = ex0 + nw * nw;  // unused guard
+      (void)cp_;
+      // forward elimination on a private copy: store modified c' in Minv column temporarily
+      double cprev = 0.0, dprev = 0.0;
+      for (int w = 0; w < nw; w++) {
+        double Pw = l3[0 * nw + w], Dw = l3[1 * nw + w], Nw = l3[2 * nw + w];
+        double lo = (w > 0) ? -Pw * l3[5 * nw + w] : 0.0;                       // M[w][w-1]
+        double di = Dw - Pw * l3[6 * nw + w] - ((w + 1 < nw) ? Nw * l3[3 * nw + w + 1] : 0.0);
+        double up = (w + 1 < nw) ? -Nw * l3[4 * nw + w + 1] : 0.0;              // M[w][w+1]
+        double rhs = (w == t) ? 1.0 : 0.0;
+        double den = di - lo * cprev;
+        double cc = up / den;
+        double dd = (rhs - lo * dprev) / den;
+        col[w * nw + t] = cc;          // c'
+        Minv[w * nw + t] = dd;         // d'
+        cprev = cc; dprev = dd;
+      }
+      double xn = 0.0;
+      for (int w = nw - 1; w >= 0; w--) {
+        double xv = Minv[w * nw + t] - col[w * nw + t] * xn;
+        Minv[w * nw + t] = xv;
+        xn = xv;
+      }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ initial condition
+    // q = 1 on interior nodes, 0 on walls / padding (drivescft.cc:120-127, 1D_FEM.c:114-129)
+    double q[C], phi[C];
+#pragma unroll
+    for (int k = 0; k < C; k++) { q[k] = (t * C + k < P.ni) ? 1.0 : 0.0; phi[k] = 0.0; }
+    double XL = (t > 0 && t * C - 1 < P.ni) ? 1.0 : 0.0;                       // value at the left separator
+    double qn = ((t + 1) * C < P.ni) ? 1.0 : 0.0;          // first node of the next chunk
+    double *hb = P.hist + (size_t)(P.store_full ? p : blockIdx.x) * P.hist_stride;
+#pragma unroll
+    for (int k = 0; k < C; k++) hb[(size_t)k * T + t] = q[k];
+
+    // ------------------------------------------------------------------ the contour march
+    for (int j = 1; j <= n; j++) {
+      const bool pairing = (2 * j > n);
+      double qo[C];
+      if (pairing) {
+        const double *hs = hb + (size_t)(n - j) * SL;
+#pragma unroll
+        for (int k = 0; k < C; k++) qo[k] = hs[(size_t)k * T + t];
+      }
+      // right-hand side b = A q (pre-scaled by the pivots on chunk nodes), level-1 solve
+      double z[CA];
+      double zlast = 0.0, z0 = 0.0;
+      if constexpr (CI > 0) {
+#pragma unroll
+        for (int k = 0; k < CI; k++) {
+          double qm = (k == 0) ? XL : q[k - 1], qp = q[k + 1];
+          double bk = UNI ? fma(ca[k], qm + qp, cd[k] * q[k]) : fma(ca[k], qm, fma(cu[k], qp, cd[k] * q[k]));
+          z[k] = (k == 0) ? bk : fma(-al[k], z[k - 1], bk);
+        }
+#pragma unroll
+        for (int k = CI - 2; k >= 0; k--) z[k] = fma(-be[k], z[k + 1], z[k]);
+        zlast = z[CI - 1]; z0 = z[0];
+      }
+      const double qprev = (CI > 0) ? q[CI > 0 ? CI - 1 : 0] : XL;
+      double r = fma(sAl, qprev, sAd * q[C - 1]);
+      if constexpr (CI > 0) r = fma(-sl, zlast, r);
+      double rsep = r;                                    // lane 31: without next-warp terms
+      {
+        double zfn = shfl_dn_d(z0, 1);
+        r = fma(sAu, qn, r);
+        if constexpr (CI > 0) r = fma(-su, zfn, r);
+      }
+      if (lane == 31) r = 0.0;
+      // level 2
+      double Z;
+      {
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+          const int d = 1 << s;
+          double rm = shfl_up_d(r, d), rp = shfl_dn_d(r, d);
+          r = fma(pa_[s], rm, fma(pg_[s], rp, r));
+        }
+        Z = r * binv;
+      }
+      // level 3: publish, one barrier, redundant tiny solve
+      double *pb = pub + (j & 1) * nw * PUB + wid * PUB;
+      if (lane == 0) { pb[0] = q[0]; pb[1] = z0; pb[2] = Z; }
+      if (lane == 30) pb[3] = Z;
+      if (lane == 31) pb[4] = rsep;
+      __syncthreads();
+      double Wm = 0.0, Ww = 0.0;
+      {
+        const double *pp = pub + (j & 1) * nw * PUB;
+        for (int v = 0; v < nw; v++) {
+          double R = pp[v * PUB + 4] - l3[0 * nw + v] * pp[v * PUB + 3];
+          if (v + 1 < nw) {
+            const double *pn = pp + (v + 1) * PUB;
+            R = fma(l3[7 * nw + v], pn[0], R);
+            R = fma(-l3[8 * nw + v], pn[1], R);
+            R = fma(-l3[2 * nw + v], pn[2], R);
+          }
+          Ww = fma(Minv[wid * nw + v], R, Ww);
+          if (wid > 0) Wm = fma(Minv[(wid - 1) * nw + v], R, Wm);
+        }
+      }
+      double X = (lane == 31) ? Ww : fma(-GL, Wm, fma(-GR, Ww, Z));
+      double XLn = shfl_up_d(X, 1);
+      if (lane == 0) XLn = Wm;
+      // level-1 correction
+      if constexpr (CI > 0) {
+#pragma unroll
+        for (int k = 0; k < CI; k++) q[k] = fma(-gl[k], XLn, fma(-gr[k], X, z[k]));
+      }
+      q[C - 1] = X;
+      XL = XLn;
+      qn = shfl_dn_d(q[0], 1);
+      if (lane == 31) qn = 0.0;   // supplied through the publish buffer
+      // history + fused quadrature
+      if (P.store_full || 2 * j < n) {
+        double *hs = hb + (size_t)j * SL;
+#pragma unroll
+        for (int k = 0; k < C; k++) hs[(size_t)k * T + t] = q[k];
+      }
+      if (pairing) {
+        const double w2 = 2.0 * __ldg(P.w + j);
+#pragma unroll
+        for (int k = 0; k < C; k++) phi[k] = fma(w2 * q[k], qo[k], phi[k]);
+      } else if (2 * j == n) {
+        const double w1 = __ldg(P.w + j);
+#pragma unroll
+        for (int k = 0; k < C; k++) phi[k] = fma(w1 * q[k], q[k], phi[k]);
+      }
+    }
+
+    // ------------------------------------------------------------------ residual, phi, Q
+    double qsum = 0.0;
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+      const int g = t * C + k;
+      if (g < P.ni) {
+        const int i = g + 1;
+        const double f0 = P.f0[(size_t)p * P.N + i];
+        P.out[(size_t)p * P.ni + g] = P.sign * (f0 - phi[k]);
+        P.phi[(size_t)p * P.N + i] = phi[k];
+        double hw;
+        if (P.uniform) hw = L / (P.N - 1);
+        else { const double *x = P.x + (size_t)p * P.N; hw = 0.5 * ((x[i] - x[i - 1]) + (x[i + 1] - x[i])); }
+        qsum += (P.uniform ? 0.5 * (hw + hw) : hw) * q[k];
+        if (P.eta_full) P.eta_full[(size_t)p * P.N + i] = P.eta_mid[(size_t)p * P.ni + g];
+      }
+    }
+    if (t == 0) {
+      P.phi[(size_t)p * P.N] = 0.0; P.phi[(size_t)p * P.N + P.N - 1] = 0.0;
+      if (P.eta_full) {
+        P.eta_full[(size_t)p * P.N] = eta_node(P, p, 0, L);
+        P.eta_full[(size_t)p * P.N + P.N - 1] = eta_node(P, p, P.N - 1, L);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, d);
+    if (lane == 0) red[wid] = qsum;
+    __syncthreads();
+    if (t == 0) {
+      double s = 0.0;
+      for (int w = 0; w < nw; w++) s += red[w];
+      double len = P.uniform ? L : (P.x[(size_t)p * P.N + P.N - 1] - P.x[(size_t)p * P.N]);
+      P.Q[p] = s / len;
+    }
+  }
+}
+
+}  // namespace scftb

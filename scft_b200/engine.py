@@ -1,0 +1,161 @@
+"""ctypes host mirror of include/scft_b200.h.
+
+Engine mirrors the role of SCFT::HeatEquation<2> (DEALII_SCFT/include/SCFT.h:117-155): construct
+with (tau, N, total_time_step, L) semantics, call run()/residual() with the interior field.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libscft_b200.so")
+
+IE_ROWSCALE, IE_CONSISTENT, IRK4_CONSISTENT = 0, 1, 2
+QUAD_ROMBERG, QUAD_TRAPEZOID = 0, 1
+TAU_REF = 5.30252230020752e-01   # drivescft.cc:269
+L_REF = 3.72374357332160
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+FUNC = C.CFUNCTYPE(None, C.c_int, _dp, _dp)
+
+
+class ScftError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [("scheme", C.c_int), ("N", C.c_int), ("nsteps", C.c_int), ("quadrature", C.c_int),
+                ("sign", C.c_double), ("max_batch", C.c_int), ("device", C.c_int), ("store_history", C.c_int)]
+
+
+_lib = None
+
+# every symbol include/scft_b200.h declares
+EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_count", "scftb_set_problem",
+           "scftb_residual", "scftb_residual_batch", "scftb_residual_batch_device", "scftb_get_phi", "scftb_get_Q",
+           "scftb_get_f0_given", "scftb_get_eta_full", "scftb_get_q_history", "scftb_free_energy",
+           "scftb_bind_global", "scftb_callback_nr1", "scftb_callback_c0", "scftb_callback_fixedpoint_c0",
+           "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_adm_chen_batch"]
+
+
+def lib():
+    """Load the C-ABI library; raise if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ScftError(f"{LIB_PATH} is missing: build it with `make -C scft_b200/csrc` "
+                            "(or python -c 'import __graft_entry__ as g; g.build()')")
+        L = C.CDLL(LIB_PATH)
+        L.scftb_last_error.restype = C.c_char_p
+        L.scftb_launch_count.restype = C.c_long
+        L.scftb_launch_count.argtypes = [C.c_int]
+        L.scftb_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
+        L.scftb_destroy.argtypes = [C.c_void_p]
+        L.scftb_set_problem.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, _dp]
+        L.scftb_residual.argtypes = [C.c_void_p, _dp, _dp]
+        L.scftb_residual_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.scftb_residual_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        for nm in ("scftb_get_phi", "scftb_get_f0_given", "scftb_get_eta_full", "scftb_get_q_history", "scftb_get_Q"):
+            getattr(L, nm).argtypes = [C.c_void_p, C.c_int, _dp]
+        L.scftb_free_energy.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp]
+        L.scftb_bind_global.argtypes = [C.c_void_p]
+        for nm in ("scftb_callback_nr1", "scftb_callback_c0", "scftb_callback_fixedpoint_c0"):
+            getattr(L, nm).restype = None
+        L.scftb_adm_chen.argtypes = [C.c_void_p, _dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
+        L.scftb_adm.argtypes = [C.c_void_p, _dp, C.c_int, _ip, C.c_int]
+        L.scftb_broydn.argtypes = [C.c_void_p, _dp, C.c_int, _ip, _dp, _ip]
+        L.scftb_adm_chen_batch.argtypes = [C.c_void_p, C.c_int, _dp, C.c_double, C.c_int, C.c_double, C.c_int,
+                                           C.c_int, _ip, _dp]
+        _lib = L
+    return _lib
+
+
+def launch_count(reset=False):
+    return lib().scftb_launch_count(1 if reset else 0)
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _chk(rc):
+    if rc != 0:
+        raise ScftError(f"scft_b200 error {rc}: {lib().scftb_last_error().decode()}")
+
+
+class Engine:
+    def __init__(self, N, nsteps=2048, scheme=IE_CONSISTENT, tau=TAU_REF, L=L_REF, quadrature=QUAD_ROMBERG,
+                 sign=1.0, max_batch=1, device=0, store_history=False, x=None):
+        self.N, self.ni, self.nsteps, self.max_batch = N, N - 2, nsteps, max_batch
+        cfg = _Config(scheme, N, nsteps, quadrature, sign, max_batch, device, int(store_history))
+        h = C.c_void_p()
+        _chk(lib().scftb_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.set_problem(-1, tau, L, x)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().scftb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_problem(self, p, tau, L, x=None):
+        xa = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+        _chk(lib().scftb_set_problem(self._h, p, tau, L, _p(xa) if xa is not None else None))
+
+    def residual(self, eta_mid):
+        """host eta_mid [ni] or [nprob, ni] -> residual of the same shape (H2D + kernel + D2H)."""
+        eta = np.ascontiguousarray(eta_mid, dtype=np.float64)
+        out = np.empty_like(eta)
+        nprob = 1 if eta.ndim == 1 else eta.shape[0]
+        assert eta.shape[-1] == self.ni
+        _chk(lib().scftb_residual_batch(self._h, nprob, _p(eta), _p(out)))
+        return out
+
+    run = residual  # HeatEquation<dim>::run (drivescft.cc:81)
+
+    def residual_device(self, nprob, d_eta_ptr, d_out_ptr, stream_ptr=0):
+        _chk(lib().scftb_residual_batch_device(self._h, nprob, C.c_void_p(d_eta_ptr), C.c_void_p(d_out_ptr),
+                                               C.c_void_p(stream_ptr)))
+
+    def _get(self, fn, p, n):
+        a = np.empty(n)
+        _chk(fn(self._h, p, _p(a)))
+        return a
+
+    def phi(self, p=0):
+        return self._get(lib().scftb_get_phi, p, self.N)
+
+    def Q(self, p=0):
+        return float(self._get(lib().scftb_get_Q, p, 1)[0])
+
+    def f0_given(self, p=0):
+        return self._get(lib().scftb_get_f0_given, p, self.N)
+
+    def eta_full(self, p=0):
+        return self._get(lib().scftb_get_eta_full, p, self.N)
+
+    def q_history(self, p=0):
+        return self._get(lib().scftb_get_q_history, p, self.N * (self.nsteps + 1)).reshape(self.N, self.nsteps + 1)
+
+    def free_energy(self, p=0, f0bar=0.892581217773656):
+        F = C.c_double(0)
+        _chk(lib().scftb_free_energy(self._h, p, f0bar, C.byref(F)))
+        return F.value
+
+    def bind_global(self):
+        _chk(lib().scftb_bind_global(self._h))
+
+    def adm_chen_batch(self, x, tol, max_iteration, lmd, nn, final=False):
+        x = np.ascontiguousarray(x, dtype=np.float64).copy()
+        nprob = 1 if x.ndim == 1 else x.shape[0]
+        iters = np.zeros(nprob, dtype=np.int32)
+        err = np.zeros(nprob)
+        rc = lib().scftb_adm_chen_batch(self._h, nprob, _p(x), tol, max_iteration, lmd, nn, int(final),
+                                        iters.ctypes.data_as(_ip), _p(err))
+        if rc not in (0, 4):
+            _chk(rc)
+        return rc, x, iters, err
