@@ -123,6 +123,25 @@ int scftb_broydn(scftb_func f, double *x, int n, int *check, double *err, int *j
 int scftb_adm_chen_batch(scftb_engine *e, int nprob, double *x, double tol, int maxIteration,
                          double lmd, int nn, int Final, int *iters_out, double *err_out);
 
+/* The same, one iteration at a time, for callers that keep the fields on the device (sweeps,
+ * benchmarks).  A mixer owns the per-problem history rings X,Y (ADM_chen_C.c:49-50), lk and the
+ * restart index.  scftb_mixer_iterate_device issues Y_k = F(X_k) and the Anderson update on the
+ * caller's stream and returns immediately; converged problems are frozen and skipped. */
+typedef struct scftb_mixer scftb_mixer;
+int scftb_mixer_create(scftb_engine *e, int nprob, double tol, double lmd, int nn, int Final, scftb_mixer **out);
+int scftb_mixer_destroy(scftb_mixer *m);
+int scftb_mixer_reset(scftb_mixer *m, const double *x, int x_is_device, void *stream);
+int scftb_mixer_iterate_device(scftb_mixer *m, void *stream);
+/* done[p]: 0 running, 1 converged, 2 NaN; iters[p]: iteration index at which it stopped; err[p]: last max|F| */
+int scftb_mixer_status(scftb_mixer *m, void *stream, int *done, int *iters, double *err);
+int scftb_mixer_get_x(scftb_mixer *m, void *stream, double *x /* host [nprob][N-2] */);
+
+/* ---- measurement hooks ---------------------------------------------------------------------- */
+/* When on, every march-kernel launch is bracketed by CUDA events on its launching stream;
+ * scftb_get_march_ms returns the summed device time and the number of launches since the last call. */
+int scftb_set_timing(scftb_engine *e, int on);
+int scftb_get_march_ms(scftb_engine *e, double *total_ms, int *count);
+
 #ifdef __cplusplus
 }
 #endif

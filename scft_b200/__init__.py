@@ -6,4 +6,4 @@ thin Python host mirror used by tests/ and bench.py; it fails loudly if the libr
 there is no CPU fallback.
 """
 from .engine import (Engine, lib, IE_ROWSCALE, IE_CONSISTENT, IRK4_CONSISTENT, QUAD_ROMBERG,  # noqa: F401
-                     QUAD_TRAPEZOID, TAU_REF, L_REF, ScftError, launch_count, LIB_PATH)
+                     QUAD_TRAPEZOID, TAU_REF, L_REF, ScftError, launch_count, LIB_PATH, AndersonBatch)

@@ -23,13 +23,6 @@ int fail(int code, const std::string &msg) {
   return code;
 }
 
-#define CK(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t _e = (call);                                                                       \
-    if (_e != cudaSuccess)                                                                         \
-      return fail(SCFTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));             \
-  } while (0)
-
 // ---------------------------------------------------------------------------------------------
 // Romberg quadrature as a weight vector.  romint.c:21-57 builds trapezoid sums on 1,2,4,...,m
 // intervals and extrapolates the last K=5 of them to h^2 -> 0 with Neville's scheme
@@ -87,13 +80,13 @@ void f0_given(int N, const double *x, double tau, double *f0) {
 // m = 0): the reference solves the tridiagonal system densely with gaussj; here one thread per
 // problem runs Thomas over the N-2 knots.  Uniform meshes never need this (see eta_node()).
 // ---------------------------------------------------------------------------------------------
-__global__ void spline_bnd_kernel(int nprob, int N, const double *x, const double *eta_mid, double *scratch,
-                                  double *eta_bnd) {
+__global__ void spline_bnd_kernel(int nprob, int N, const double *x, const double *eta_mid, long long eta_stride,
+                                  double *scratch, double *eta_bnd) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nprob) return;
   const int Nx = N - 2;
   const double *xk = x + (size_t)p * N + 1;  // knots = interior nodes
-  const double *y = eta_mid + (size_t)p * Nx;
+  const double *y = eta_mid + (size_t)p * eta_stride;
   double *cp = scratch + (size_t)p * 2 * Nx, *dp = cp + Nx;
   // rows i=1..Nx-2: (x_i-x_{i-1})/6, (x_{i+1}-x_{i-1})/3, (x_{i+1}-x_i)/6 ; rows 0, Nx-1: M = 0
   cp[0] = 0.0; dp[0] = 0.0;
@@ -123,12 +116,6 @@ __global__ void spline_bnd_kernel(int nprob, int N, const double *x, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-typedef void (*march_fn)(MarchParams);
-struct KernelChoice {
-  int C, T;
-  march_fn fn;
-};
-
 template <int C, int TMAX, int MINB>
 static march_fn pick(bool uni) {
   return uni ? (march_fn)march_ie_kernel<C, true, TMAX, MINB> : (march_fn)march_ie_kernel<C, false, TMAX, MINB>;
@@ -159,24 +146,8 @@ static int choose_kernel(int ni, bool uni, KernelChoice &kc) {
 
 using namespace scftb;
 
-struct scftb_engine {
-  scftb_config cfg;
-  int ni;
-  bool uniform;
-  KernelChoice kc;
-  int slots;       // resident CTAs
-  int nslices;     // history slices per problem/slot
-  size_t SL;       // doubles per slice
-  cudaStream_t stream;
-  // host mirrors
-  std::vector<double> h_tau, h_L, h_x, h_f0, h_w;
-  bool params_dirty;
-  int last_nprob;
-  // device buffers
-  double *d_eta, *d_out, *d_phi, *d_Q, *d_f0, *d_L, *d_x, *d_eta_bnd, *d_w, *d_hist, *d_eta_full, *d_scratch;
-};
-
-static int upload_params(scftb_engine *e) {
+namespace scftb {
+int upload_params(scftb_engine *e) {
   if (!e->params_dirty) return SCFTB_OK;
   const int N = e->cfg.N, B = e->cfg.max_batch;
   CK(cudaMemcpyAsync(e->d_f0, e->h_f0.data(), sizeof(double) * N * B, cudaMemcpyHostToDevice, e->stream));
@@ -192,6 +163,7 @@ static int upload_params(scftb_engine *e) {
   e->params_dirty = false;
   return SCFTB_OK;
 }
+}  // namespace scftb
 
 extern "C" {
 
@@ -214,6 +186,7 @@ int scftb_create(const scftb_config *cfg, scftb_engine **out) {
   e->uniform = true;
   e->params_dirty = true;
   e->last_nprob = 0;
+  e->timing = false;
   e->d_x = e->d_eta_bnd = e->d_scratch = nullptr;
   const int N = cfg->N, B = cfg->max_batch, n = cfg->nsteps;
   if (cfg->quadrature == SCFTB_QUAD_ROMBERG) {
@@ -269,6 +242,28 @@ int scftb_create(const scftb_config *cfg, scftb_engine **out) {
   return SCFTB_OK;
 }
 
+int scftb_set_timing(scftb_engine *e, int on) {
+  if (!e) return fail(SCFTB_ERR_ARG, "null engine");
+  e->timing = on != 0;
+  return SCFTB_OK;
+}
+
+int scftb_get_march_ms(scftb_engine *e, double *total_ms, int *count) {
+  if (!e || !total_ms || !count) return fail(SCFTB_ERR_ARG, "null argument");
+  double tot = 0.0;
+  int n = 0;
+  for (auto &ev : e->ev_pending) {
+    CK(cudaEventSynchronize(ev.second));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    tot += ms; n++;
+    e->ev_free.push_back(ev);
+  }
+  e->ev_pending.clear();
+  *total_ms = tot; *count = n;
+  return SCFTB_OK;
+}
+
 int scftb_engine_max_batch(scftb_engine *e) { return e ? e->cfg.max_batch : 0; }
 
 int scftb_destroy(scftb_engine *e) {
@@ -305,26 +300,42 @@ int scftb_set_problem(scftb_engine *e, int p, double tau, double L, const double
   return SCFTB_OK;
 }
 
-static int launch_march(scftb_engine *e, int nprob, const double *d_eta, double *d_out, cudaStream_t st) {
+}  // extern "C"
+
+namespace scftb {
+int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_stride, double *d_out,
+                 long long out_stride, const int *d_skip, cudaStream_t st) {
   MarchParams P;
   P.N = e->cfg.N; P.ni = e->ni; P.nsteps = e->cfg.nsteps;
   P.scheme = e->cfg.scheme; P.nprob = nprob; P.store_full = e->cfg.store_history;
   P.uniform = e->uniform ? 1 : 0; P.sign = e->cfg.sign;
-  P.eta_mid = d_eta; P.f0 = e->d_f0; P.L = e->d_L; P.x = e->d_x; P.eta_bnd = e->d_eta_bnd; P.w = e->d_w;
+  P.eta_mid = d_eta; P.eta_stride = eta_stride; P.out_stride = out_stride; P.skip = d_skip;
+  P.f0 = e->d_f0; P.L = e->d_L; P.x = e->d_x; P.eta_bnd = e->d_eta_bnd; P.w = e->d_w;
   P.hist = e->d_hist; P.hist_stride = (long long)e->nslices * (long long)e->SL;
   P.out = d_out; P.phi = e->d_phi; P.Q = e->d_Q; P.eta_full = e->d_eta_full;
   if (!e->uniform) {
-    spline_bnd_kernel<<<(nprob + 63) / 64, 64, 0, st>>>(nprob, P.N, e->d_x, d_eta, e->d_scratch, e->d_eta_bnd);
+    spline_bnd_kernel<<<(nprob + 63) / 64, 64, 0, st>>>(nprob, P.N, e->d_x, d_eta, eta_stride, e->d_scratch,
+                                                          e->d_eta_bnd);
     g_launches++;
   }
   int grid = std::min(nprob, e->slots);
   size_t smem = sizeof(double) * SmemLayout::doubles(e->kc.T);
+  std::pair<cudaEvent_t, cudaEvent_t> ev;
+  if (e->timing) {
+    if (!e->ev_free.empty()) { ev = e->ev_free.back(); e->ev_free.pop_back(); }
+    else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
+    CK(cudaEventRecord(ev.first, st));
+  }
   e->kc.fn<<<grid, e->kc.T, smem, st>>>(P);
+  if (e->timing) { CK(cudaEventRecord(ev.second, st)); e->ev_pending.push_back(ev); }
   g_launches++;
   CK(cudaGetLastError());
   e->last_nprob = nprob;
   return SCFTB_OK;
 }
+}  // namespace scftb
+
+extern "C" {
 
 int scftb_residual_batch_device(scftb_engine *e, int nprob, const double *d_eta_mid, double *d_out, void *stream) {
   if (!e || nprob < 1 || nprob > e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "nprob out of range");
@@ -335,7 +346,7 @@ int scftb_residual_batch_device(scftb_engine *e, int nprob, const double *d_eta_
     if (rc) return rc;
     CK(cudaStreamSynchronize(e->stream));
   }
-  return launch_march(e, nprob, d_eta_mid, d_out, st);
+  return launch_march(e, nprob, d_eta_mid, e->ni, d_out, e->ni, nullptr, st);
 }
 
 int scftb_residual_batch(scftb_engine *e, int nprob, const double *eta_mid, double *out) {
@@ -345,7 +356,7 @@ int scftb_residual_batch(scftb_engine *e, int nprob, const double *eta_mid, doub
   if (rc) return rc;
   const size_t bytes = sizeof(double) * (size_t)e->ni * nprob;
   CK(cudaMemcpyAsync(e->d_eta, eta_mid, bytes, cudaMemcpyHostToDevice, e->stream));
-  rc = launch_march(e, nprob, e->d_eta, e->d_out, e->stream);
+  rc = launch_march(e, nprob, e->d_eta, e->ni, e->d_out, e->ni, nullptr, e->stream);
   if (rc) return rc;
   CK(cudaMemcpyAsync(out, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -428,12 +439,6 @@ int scftb_free_energy(scftb_engine *e, int p, double f0bar, double *F) {
   }
   *F = (I / f0bar / L + std::log(f0bar)) / (-1000.);  // scft.cc:446-447
   return SCFTB_OK;
-}
-
-int scftb_adm_chen_batch(scftb_engine *e, int nprob, double *x, double tol, int maxIteration, double lmd, int nn,
-                         int Final, int *iters_out, double *err_out) {
-  (void)e; (void)nprob; (void)x; (void)tol; (void)maxIteration; (void)lmd; (void)nn; (void)Final; (void)iters_out; (void)err_out;
-  return fail(SCFTB_ERR_STATE, "scftb_adm_chen_batch: not built yet");
 }
 
 }  // extern "C"

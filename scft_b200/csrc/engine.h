@@ -1,5 +1,9 @@
 // engine.h — internal declarations shared by the C-ABI translation units.
 #pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -11,6 +15,51 @@ int romberg_weights(int m, double hh, std::vector<double> &w);
 void trapezoid_weights(int m, double hh, std::vector<double> &w);
 void f0_given(int N, const double *x, double tau, double *f0);
 int gauss_jordan(std::vector<double> &a, int n, std::vector<double> &b, bool nudge);
+}  // namespace scftb
+
+namespace scftb {
+struct MarchParams;
+typedef void (*march_fn)(MarchParams);
+struct KernelChoice {
+  int C, T;
+  march_fn fn;
+};
+extern std::atomic<long> g_launches;
+}  // namespace scftb
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return scftb::fail(SCFTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));             \
+  } while (0)
+
+
+struct scftb_engine {
+  scftb_config cfg;
+  int ni;
+  bool uniform;
+  scftb::KernelChoice kc;
+  int slots;       // resident CTAs
+  int nslices;     // history slices per problem/slot
+  size_t SL;       // doubles per slice
+  cudaStream_t stream;
+  // host mirrors
+  std::vector<double> h_tau, h_L, h_x, h_f0, h_w;
+  bool params_dirty;
+  int last_nprob;
+  // device buffers
+  double *d_eta, *d_out, *d_phi, *d_Q, *d_f0, *d_L, *d_x, *d_eta_bnd, *d_w, *d_hist, *d_eta_full, *d_scratch;
+  // optional per-launch timing of the march kernel (CUDA events on the launching stream)
+  bool timing;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+};
+
+namespace scftb {
+// launch one batch of residual evaluations; eta/out are device pointers with the given problem strides
+int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_stride, double *d_out,
+                 long long out_stride, const int *d_skip, cudaStream_t st);
+int upload_params(scftb_engine *e);
 }  // namespace scftb
 
 // internal accessor (not part of the public ABI)

@@ -37,7 +37,10 @@ struct MarchParams {
   int store_full;         // 1: store every slice, per problem; 0: half history, per CTA slot
   int uniform;            // 1: uniform mesh (x == nullptr)
   double sign;
-  const double *eta_mid;  // [nprob][ni]
+  const double *eta_mid;  // [nprob][ni], problem stride eta_stride
+  long long eta_stride;   // doubles between consecutive problems in eta_mid
+  long long out_stride;   // same for out
+  const int *skip;        // [nprob] non-zero: leave the problem untouched (converged) or nullptr
   const double *f0;       // [nprob][N]
   const double *L;        // [nprob]
   const double *x;        // [nprob][N] node coordinates (non-uniform) or nullptr
@@ -59,7 +62,7 @@ __device__ __forceinline__ double shfl_d(double v, int l) { return __shfl_sync(0
 // (scft.cc:456-475 -> spline_chen.c:77-100).  With y''=0 at the end knots the cubic term of the
 // first/last piece vanishes on a uniform mesh, leaving the linear extrapolation a*y0+b*y1.
 __device__ __forceinline__ double eta_node(const MarchParams &P, int p, int i, double L) {
-  const double *em = P.eta_mid + (size_t)p * P.ni;
+  const double *em = P.eta_mid + (size_t)p * P.eta_stride;
   if (i >= 1 && i <= P.N - 2) return em[i - 1];
   if (!P.uniform) return P.eta_bnd[2 * p + (i == 0 ? 0 : 1)];
   const int N = P.N;
@@ -140,6 +143,7 @@ __global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
   const int SL = T * C;                 // doubles per history slice
 
   for (int p = blockIdx.x; p < P.nprob; p += gridDim.x) {
+    if (P.skip && P.skip[p]) continue;
     const double L = P.L[p];
     // ------------------------------------------------------------------ assembly + level 1
     double ca[CA], cd[CA], cu[CA];      // pre-scaled rows of A on chunk-interior nodes (UNI: ca==cu)
@@ -369,13 +373,13 @@ __global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
       if (g < P.ni) {
         const int i = g + 1;
         const double f0 = P.f0[(size_t)p * P.N + i];
-        P.out[(size_t)p * P.ni + g] = P.sign * (f0 - phi[k]);
+        P.out[(size_t)p * P.out_stride + g] = P.sign * (f0 - phi[k]);
         P.phi[(size_t)p * P.N + i] = phi[k];
         double hw;
         if (P.uniform) hw = L / (P.N - 1);
         else { const double *x = P.x + (size_t)p * P.N; hw = 0.5 * ((x[i] - x[i - 1]) + (x[i + 1] - x[i])); }
         qsum += (P.uniform ? 0.5 * (hw + hw) : hw) * q[k];
-        if (P.eta_full) P.eta_full[(size_t)p * P.N + i] = P.eta_mid[(size_t)p * P.ni + g];
+        if (P.eta_full) P.eta_full[(size_t)p * P.N + i] = P.eta_mid[(size_t)p * P.eta_stride + g];
       }
     }
     if (t == 0) {

@@ -37,7 +37,9 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_residual", "scftb_residual_batch", "scftb_residual_batch_device", "scftb_get_phi", "scftb_get_Q",
            "scftb_get_f0_given", "scftb_get_eta_full", "scftb_get_q_history", "scftb_free_energy",
            "scftb_bind_global", "scftb_callback_nr1", "scftb_callback_c0", "scftb_callback_fixedpoint_c0",
-           "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_adm_chen_batch"]
+           "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_adm_chen_batch",
+           "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
+           "scftb_mixer_status", "scftb_mixer_get_x", "scftb_set_timing", "scftb_get_march_ms"]
 
 
 def lib():
@@ -68,6 +70,15 @@ def lib():
         L.scftb_broydn.argtypes = [C.c_void_p, _dp, C.c_int, _ip, _dp, _ip]
         L.scftb_adm_chen_batch.argtypes = [C.c_void_p, C.c_int, _dp, C.c_double, C.c_int, C.c_double, C.c_int,
                                            C.c_int, _ip, _dp]
+        L.scftb_mixer_create.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                         C.POINTER(C.c_void_p)]
+        L.scftb_mixer_destroy.argtypes = [C.c_void_p]
+        L.scftb_mixer_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.scftb_mixer_iterate_device.argtypes = [C.c_void_p, C.c_void_p]
+        L.scftb_mixer_status.argtypes = [C.c_void_p, C.c_void_p, _ip, _ip, _dp]
+        L.scftb_mixer_get_x.argtypes = [C.c_void_p, C.c_void_p, _dp]
+        L.scftb_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.scftb_get_march_ms.argtypes = [C.c_void_p, _dp, _ip]
         _lib = L
     return _lib
 
@@ -117,6 +128,19 @@ class Engine:
 
     run = residual  # HeatEquation<dim>::run (drivescft.cc:81)
 
+    def residual_host_ptr(self, nprob, h_eta_ptr, h_out_ptr):
+        """scftb_residual_batch on caller-owned (e.g. pinned) host buffers given as addresses"""
+        _chk(lib().scftb_residual_batch(self._h, nprob, C.cast(h_eta_ptr, _dp), C.cast(h_out_ptr, _dp)))
+
+    def set_timing(self, on=True):
+        _chk(lib().scftb_set_timing(self._h, int(on)))
+
+    def march_ms(self):
+        """(total device ms, launches) of the march kernel since the last call"""
+        tot, cnt = C.c_double(0), C.c_int(0)
+        _chk(lib().scftb_get_march_ms(self._h, C.byref(tot), C.byref(cnt)))
+        return tot.value, cnt.value
+
     def residual_device(self, nprob, d_eta_ptr, d_out_ptr, stream_ptr=0):
         _chk(lib().scftb_residual_batch_device(self._h, nprob, C.c_void_p(d_eta_ptr), C.c_void_p(d_out_ptr),
                                                C.c_void_p(stream_ptr)))
@@ -159,3 +183,43 @@ class Engine:
         if rc not in (0, 4):
             _chk(rc)
         return rc, x, iters, err
+
+
+class AndersonBatch:
+    """Device-resident Anderson mixing of a batch (scftb_mixer_*): adm_chen per problem."""
+
+    def __init__(self, eng, nprob, tol=1e-7, lmd=0.9, nn=3, final=False):
+        self.eng, self.nprob = eng, nprob
+        h = C.c_void_p()
+        _chk(lib().scftb_mixer_create(eng._h, nprob, tol, lmd, nn, int(final), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().scftb_mixer_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        _chk(lib().scftb_mixer_reset(self._h, C.c_void_p(x.ctypes.data), 0, None))
+
+    def reset_device(self, d_x_ptr, stream_ptr=0):
+        _chk(lib().scftb_mixer_reset(self._h, C.c_void_p(d_x_ptr), 1, C.c_void_p(stream_ptr)))
+
+    def iterate_device(self, stream_ptr=0):
+        _chk(lib().scftb_mixer_iterate_device(self._h, C.c_void_p(stream_ptr)))
+
+    def status(self, stream_ptr=0):
+        done = np.zeros(self.nprob, dtype=np.int32)
+        iters = np.zeros(self.nprob, dtype=np.int32)
+        err = np.zeros(self.nprob)
+        _chk(lib().scftb_mixer_status(self._h, C.c_void_p(stream_ptr), done.ctypes.data_as(_ip),
+                                      iters.ctypes.data_as(_ip), _p(err)))
+        return done, iters, err
+
+    def x(self, stream_ptr=0):
+        out = np.zeros((self.nprob, self.eng.ni))
+        _chk(lib().scftb_mixer_get_x(self._h, C.c_void_p(stream_ptr), _p(out)))
+        return out
