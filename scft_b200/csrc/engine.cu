@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -116,28 +117,32 @@ __global__ void spline_bnd_kernel(int nprob, int N, const double *x, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int C, int TMAX, int MINB>
+template <int C, int T, int MINB>
 static march_fn pick(bool uni) {
-  return uni ? (march_fn)march_ie_kernel<C, true, TMAX, MINB> : (march_fn)march_ie_kernel<C, false, TMAX, MINB>;
+  return uni ? (march_fn)march_ie_kernel<C, T, true, MINB> : (march_fn)march_ie_kernel<C, T, false, MINB>;
 }
 
-// nodes per thread C and threads per problem T for ni interior nodes
-static int choose_kernel(int ni, bool uni, KernelChoice &kc) {
+// nodes per thread C and threads per problem T for ni interior nodes.  SCFTB_FORCE_C=4 selects the
+// 256-thread / 4-nodes-per-thread variant where it applies (tuning experiments).
+int choose_kernel(int ni, bool uni, KernelChoice &kc) {
   int C = 1;
   while (C < 16 && (ni + C - 1) / C > 128) C *= 2;
-  int T = ((ni + C - 1) / C + 31) / 32 * 32;
-  int tmax = 128;
-  switch (C) {
-    case 1: kc.fn = pick<1, 128, 4>(uni); break;
-    case 2: kc.fn = pick<2, 128, 4>(uni); break;
-    case 4: kc.fn = pick<4, 128, 4>(uni); break;
-    case 8: kc.fn = pick<8, 128, 3>(uni); break;
-    default:
-      if (T <= 128) kc.fn = pick<16, 128, 1>(uni);
-      else { kc.fn = pick<16, 256, 1>(uni); tmax = 256; }
-      break;
-  }
-  if (T > tmax) return 1;
+  const char *force = getenv("SCFTB_FORCE_C");
+  if (force && atoi(force) == 4 && C == 8) C = 4;
+  int need = (ni + C - 1) / C;
+  int T = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 256));
+  if (need > 256) return 1;
+  kc.fn = nullptr;
+  if (C == 1 && T == 32) kc.fn = pick<1, 32, 8>(uni);
+  if (C == 1 && T == 64) kc.fn = pick<1, 64, 6>(uni);
+  if (C == 1 && T == 128) kc.fn = pick<1, 128, 4>(uni);
+  if (C == 2 && T == 128) kc.fn = pick<2, 128, 4>(uni);
+  if (C == 4 && T == 128) kc.fn = pick<4, 128, 4>(uni);
+  if (C == 4 && T == 256) kc.fn = pick<4, 256, 2>(uni);
+  if (C == 8 && T == 128) kc.fn = pick<8, 128, 3>(uni);
+  if (C == 16 && T == 128) kc.fn = pick<16, 128, 1>(uni);
+  if (C == 16 && T == 256) kc.fn = pick<16, 256, 1>(uni);
+  if (!kc.fn) return 1;
   kc.C = C; kc.T = T;
   return 0;
 }
@@ -196,6 +201,10 @@ int scftb_create(const scftb_config *cfg, scftb_engine **out) {
     }
   } else
     trapezoid_weights(n, 1.0 / n, e->h_w);
+  // pair weights for the fused half-history quadrature: the weights are symmetric (w_j = w_{n-j}), so
+  // sum_j w_j q_j q_{n-j} = sum_{j>n/2} 2 w_j q_j q_{n-j} + [n even] w_{n/2} q_{n/2}^2
+  std::vector<double> wq(e->h_w);
+  for (int j = 0; j <= n; j++) wq[j] = (2 * j > n) ? 2.0 * e->h_w[j] : ((2 * j == n) ? e->h_w[j] : 0.0);
   if (choose_kernel(e->ni, true, e->kc)) {
     delete e;
     return fail(SCFTB_ERR_ARG, "N too large for the register-resident march (N <= 4098 in this build)");
@@ -214,13 +223,7 @@ int scftb_create(const scftb_config *cfg, scftb_engine **out) {
   e->SL = (size_t)e->kc.T * e->kc.C;
   int sms = 0, occ = 0;
   CKD(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-  size_t smem = sizeof(double) * SmemLayout::doubles(e->kc.T);
-  for (int uni = 0; uni < 2; uni++) {
-    KernelChoice k2;
-    choose_kernel(e->ni, uni, k2);
-    CKD(cudaFuncSetAttribute((const void *)k2.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)e->kc.fn, e->kc.T, smem));
+  CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)e->kc.fn, e->kc.T, 0));
   if (occ < 1) occ = 1;
   e->slots = std::min(B, sms * occ);
   e->nslices = cfg->store_history ? n + 1 : n / 2 + 1;
@@ -237,7 +240,7 @@ int scftb_create(const scftb_config *cfg, scftb_engine **out) {
   CKD(cudaMalloc(&e->d_L, sizeof(double) * B));
   CKD(cudaMalloc(&e->d_w, sizeof(double) * (n + 1)));
   CKD(cudaMalloc(&e->d_hist, sizeof(double) * nh));
-  CKD(cudaMemcpy(e->d_w, e->h_w.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice));
+  CKD(cudaMemcpy(e->d_w, wq.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice));
   *out = e;
   return SCFTB_OK;
 }
@@ -319,14 +322,13 @@ int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_
     g_launches++;
   }
   int grid = std::min(nprob, e->slots);
-  size_t smem = sizeof(double) * SmemLayout::doubles(e->kc.T);
   std::pair<cudaEvent_t, cudaEvent_t> ev;
   if (e->timing) {
     if (!e->ev_free.empty()) { ev = e->ev_free.back(); e->ev_free.pop_back(); }
     else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
     CK(cudaEventRecord(ev.first, st));
   }
-  e->kc.fn<<<grid, e->kc.T, smem, st>>>(P);
+  e->kc.fn<<<grid, e->kc.T, 0, st>>>(P);
   if (e->timing) { CK(cudaEventRecord(ev.second, st)); e->ev_pending.push_back(ev); }
   g_launches++;
   CK(cudaGetLastError());
@@ -401,7 +403,7 @@ int scftb_get_q_history(scftb_engine *e, int p, double *hist) {
   for (int j = 0; j <= n; j++)
     for (int g = 0; g < e->ni; g++) {
       int t = g / C, k = g % C;
-      hist[(size_t)(g + 1) * (n + 1) + j] = raw[(size_t)j * e->SL + (size_t)k * T + t];
+      hist[(size_t)(g + 1) * (n + 1) + j] = raw[(size_t)j * e->SL + hist_index(C, T, t, k)];
     }
   return SCFTB_OK;
 }

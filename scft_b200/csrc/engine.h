@@ -25,6 +25,7 @@ struct KernelChoice {
   march_fn fn;
 };
 extern std::atomic<long> g_launches;
+int choose_kernel(int ni, bool uni, KernelChoice &kc);
 }  // namespace scftb
 
 #define CK(call)                                                                                   \

@@ -58,6 +58,19 @@ __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_
 __device__ __forceinline__ double shfl_dn_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double shfl_d(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
 
+// Ampere-style asynchronous global->shared copies (LDGSTS)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 // eta on node i (0..N-1).  Wall nodes: natural-spline extrapolation of the interior values
 // (scft.cc:456-475 -> spline_chen.c:77-100).  With y''=0 at the end knots the cubic term of the
 // first/last piece vanishes on a uniform mesh, leaving the linear extrapolation a*y0+b*y1.
@@ -112,35 +125,35 @@ __device__ __forceinline__ Row assemble_row(const MarchParams &P, int p, int g, 
   return r;
 }
 
-// shared-memory carve-up (doubles)
-struct SmemLayout {
-  int T, nw;
-  __host__ __device__ static int doubles(int T) {
-    int nw = T / 32;
-    return 2 * T            // setup exchange gl0 / gr0
-           + 9 * nw         // level-3 coefficients
-           + nw * nw        // Minv
-           + 2 * nw * 8     // per-step publish buffers (double-buffered)
-           + nw + 8;        // reduction scratch
-  }
-};
+// index of node k (0..C-1) of thread t inside a history slice of T*C doubles: pairs of
+// consecutive nodes of a thread are adjacent so that a warp moves 512 contiguous bytes per
+// 128-bit instruction (C = 1: 256 bytes per 64-bit instruction).
+__host__ __device__ inline int hist_index(int C, int T, int t, int k) {
+  return (C == 1) ? t : ((k >> 1) * T + t) * 2 + (k & 1);
+}
 
-constexpr int PUB = 8;  // doubles per warp in a publish buffer
+constexpr int PUB = 8;  // doubles per warp in a publish buffer: qf, zf, Z0, Z30, rsep
 
-template <int C, bool UNI, int TMAX, int MINB>
-__global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
+template <int C, int T, bool UNI, int MINB>
+__global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
+  static_assert(C == 1 || (C % 2) == 0, "C must be 1 or even");
   constexpr int CI = C - 1;             // chunk-interior nodes per thread
   constexpr int CA = CI > 0 ? CI : 1;   // array extent
-  const int t = threadIdx.x, T = blockDim.x, lane = t & 31, wid = t >> 5, nw = T >> 5;
-  extern __shared__ double sm[];
-  double *ex0 = sm, *ex1 = sm + T;
-  double *l3 = sm + 2 * T;              // [9][nw]: P D Nx GL0 GR0 GL30 GR30 cAu csu
-  double *Minv = l3 + 9 * nw;           // [nw][nw]
-  double *pub = Minv + nw * nw;         // [2][nw][PUB]
-  double *red = pub + 2 * nw * PUB;     // [nw + 8]
+  constexpr int NW = T / 32;
+  constexpr int SL = T * C;             // doubles per history slice
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  __shared__ __align__(16) double s_ex[2][T];        // setup exchange gl0 / gr0, then scratch
+  __shared__ __align__(16) double s_l3[NW][4];       // per warp separator v: P, cAu, csu, Nx
+  __shared__ __align__(16) double s_l3s[NW][6];      // setup only: D, GL0, GR0, GL30, GR30
+  __shared__ __align__(16) double s_minv[NW][NW];    // inverse of the level-3 matrix
+  __shared__ __align__(16) double s_pub[2][NW][PUB]; // per-step publish buffers (double-buffered)
+  __shared__ double s_red[NW];
+  // staging ring for the paired history slice q(., n-j): each thread cp.async's and reads back its
+  // own 16-byte pieces, so no barrier is involved
+  constexpr bool STAGE = (C * T <= 2048);   // 32 KB of static shared memory at most
+  __shared__ __align__(16) double s_qo[STAGE ? 2 : 1][STAGE ? (C + 1) / 2 : 1][STAGE ? T : 1][2];
   const int n = P.nsteps;
   const double dt = 1.0 / n;            // time_step = 1/(total_time_step-1), scft.cc:29
-  const int SL = T * C;                 // doubles per history slice
 
   for (int p = blockIdx.x; p < P.nprob; p += gridDim.x) {
     if (P.skip && P.skip[p]) continue;
@@ -155,15 +168,19 @@ __global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
     }
     if constexpr (CI > 0) {
       double Tl0 = 0, TuL = 0, pinv_prev = 0, Tu_prev = 0;
+      double alo[CA];                           // pinv_k * Tl_k (setup only)
 #pragma unroll
       for (int k = 0; k < CI; k++) {
         Row r = assemble_row(P, p, t * C + k, L, dt);
         double piv = (k == 0) ? r.Td : r.Td - (r.Tl * pinv_prev) * Tu_prev;
         double pinv = 1.0 / piv;
         // UNI: one off-diagonal coefficient serves both neighbours; the Dirichlet zeroing of A is
-        // then carried by the neighbour values themselves (wall / padding nodes are exactly 0).
+        // then carried by the neighbour values themselves (wall / padding nodes are exactly 0),
+        // and A's diagonal is 4x the off-diagonal, so no cd[] is kept.
         ca[k] = pinv * ((UNI && r.Al == 0.0) ? r.Au : r.Al); cd[k] = pinv * r.Ad; cu[k] = pinv * r.Au;
-        al[k] = (k == 0) ? 0.0 : pinv * r.Tl;
+        alo[k] = (k == 0) ? 0.0 : pinv * r.Tl;
+        // UNI: the forward sweep runs on u = y/A_off with the plain Thomas multiplier Tl_k/piv_{k-1}
+        al[k] = (k == 0) ? 0.0 : (UNI ? r.Tl * pinv_prev : alo[k]);
         be[k] = (k == CI - 1) ? 0.0 : pinv * r.Tu;
         if (k == 0) Tl0 = pinv * r.Tl;          // scaled coupling to the left separator
         if (k == CI - 1) TuL = pinv * r.Tu;     // scaled coupling to the own (right) separator
@@ -173,7 +190,7 @@ __global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
       double y[CA];
       y[0] = Tl0;
 #pragma unroll
-      for (int k = 1; k < CI; k++) y[k] = -al[k] * y[k - 1];
+      for (int k = 1; k < CI; k++) y[k] = -alo[k] * y[k - 1];
       gl[CI - 1] = y[CI - 1];
 #pragma unroll
       for (int k = CI - 2; k >= 0; k--) gl[k] = y[k] - be[k] * gl[k + 1];
@@ -183,11 +200,11 @@ __global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
     }
     // ------------------------------------------------------------------ Schur rows on separators
     double a, b, c;
-    __syncthreads();  // previous problem's readers of sm are done
+    __syncthreads();  // previous problem's readers of shared memory are done
     if constexpr (CI > 0) {
-      ex0[t] = gl[0]; ex1[t] = gr[0];
+      s_ex[0][t] = gl[0]; s_ex[1][t] = gr[0];
       __syncthreads();
-      double gl0n = (t + 1 < T) ? ex0[t + 1] : 0.0, gr0n = (t + 1 < T) ? ex1[t + 1] : 0.0;
+      double gl0n = (t + 1 < T) ? s_ex[0][t + 1] : 0.0, gr0n = (t + 1 < T) ? s_ex[1][t + 1] : 0.0;
       a = -sl * gl[CI - 1];
       b = sd - sl * gr[CI - 1] - su * gl0n;
       c = -su * gr0n;
@@ -195,8 +212,8 @@ __global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
       a = sl; b = sd; c = su;
     }
     // ------------------------------------------------------------------ level 2: warp PCR setup
-    double l3P = a, l3D = b, l3N = c;       // lane 31: row of the warp separator
-    double A0 = (lane == 0) ? a : 0.0, C30 = (lane == 30) ? c : 0.0;
+    const double l3P = a, l3D = b, l3N = c;       // lane 31: row of the warp separator
+    const double A0 = (lane == 0) ? a : 0.0, C30 = (lane == 30) ? c : 0.0;
     if (lane == 31) { a = 0.0; b = 1.0; c = 0.0; }
     if (lane == 0) a = 0.0;
     if (lane == 30) c = 0.0;
@@ -221,124 +238,152 @@ __global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
       for (int s = 0; s < 5; s++) {
         const int d = 1 << s;
         double rm = shfl_up_d(r, d), rp = shfl_dn_d(r, d);
-        r = r + pa_[s] * rm + pg_[s] * rp;
+        r = fma(pa_[s], rm, fma(pg_[s], rp, r));
       }
       return r * binv;
     };
     const double GL = pcr(A0), GR = pcr(C30);
     // ------------------------------------------------------------------ level 3 setup
-    if (lane == 31) { l3[0 * nw + wid] = l3P; l3[1 * nw + wid] = l3D; l3[2 * nw + wid] = l3N;
-                      l3[7 * nw + wid] = sAu; l3[8 * nw + wid] = (CI > 0) ? su : 0.0; }
-    if (lane == 0) { l3[3 * nw + wid] = GL; l3[4 * nw + wid] = GR; }
-    if (lane == 30) { l3[5 * nw + wid] = GL; l3[6 * nw + wid] = GR; }
+    if (lane == 31) {
+      s_l3[wid][0] = l3P; s_l3[wid][1] = sAu; s_l3[wid][2] = (CI > 0) ? su : 0.0; s_l3[wid][3] = l3N;
+      s_l3s[wid][0] = l3D;
+    }
+    if (lane == 0) { s_l3s[wid][1] = GL; s_l3s[wid][2] = GR; }
+    if (lane == 30) { s_l3s[wid][3] = GL; s_l3s[wid][4] = GR; }
     __syncthreads();
-    if (t < nw) {  // thread v: column v of M^-1 by Thomas (M is tridiagonal, diagonally dominant)
-      double *col = ex0;  // scratch [nw][nw] needs nw*nw <= 2T doubles: nw <= 64 ok
-      double *cp_ = ex0 + nw * nw;  // unused guard
-      (void)cp_;
-      // forward elimination on a private copy: store modified c' in Minv column temporarily
+    if (t < NW) {  // thread v: column v of M^-1 by Thomas (M is tridiagonal, diagonally dominant)
+      double cc[NW], dd[NW];
       double cprev = 0.0, dprev = 0.0;
-      for (int w = 0; w < nw; w++) {
-        double Pw = l3[0 * nw + w], Dw = l3[1 * nw + w], Nw = l3[2 * nw + w];
-        double lo = (w > 0) ? -Pw * l3[5 * nw + w] : 0.0;                       // M[w][w-1]
-        double di = Dw - Pw * l3[6 * nw + w] - ((w + 1 < nw) ? Nw * l3[3 * nw + w + 1] : 0.0);
-        double up = (w + 1 < nw) ? -Nw * l3[4 * nw + w + 1] : 0.0;              // M[w][w+1]
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        double Pw = s_l3[w][0], Dw = s_l3s[w][0], Nw = s_l3[w][3];
+        double lo = (w > 0) ? -Pw * s_l3s[w][3] : 0.0;                                      // M[w][w-1]
+        double di = Dw - Pw * s_l3s[w][4] - ((w + 1 < NW) ? Nw * s_l3s[(w + 1) % NW][1] : 0.0);
+        double up = (w + 1 < NW) ? -Nw * s_l3s[(w + 1) % NW][2] : 0.0;                      // M[w][w+1]
         double rhs = (w == t) ? 1.0 : 0.0;
         double den = di - lo * cprev;
-        double cc = up / den;
-        double dd = (rhs - lo * dprev) / den;
-        col[w * nw + t] = cc;          // c'
-        Minv[w * nw + t] = dd;         // d'
-        cprev = cc; dprev = dd;
+        cc[w] = up / den;
+        dd[w] = (rhs - lo * dprev) / den;
+        cprev = cc[w]; dprev = dd[w];
       }
       double xn = 0.0;
-      for (int w = nw - 1; w >= 0; w--) {
-        double xv = Minv[w * nw + t] - col[w * nw + t] * xn;
-        Minv[w * nw + t] = xv;
-        xn = xv;
+#pragma unroll
+      for (int w = NW - 1; w >= 0; w--) {
+        xn = dd[w] - cc[w] * xn;
+        s_minv[w][t] = xn;
       }
     }
     __syncthreads();
-
+    // rows wid and wid-1 of M^-1 are warp-uniform; keep them out of the loop's shared-memory traffic
+    // only when they are few
     // ------------------------------------------------------------------ initial condition
     // q = 1 on interior nodes, 0 on walls / padding (drivescft.cc:120-127, 1D_FEM.c:114-129)
     double q[C], phi[C];
 #pragma unroll
     for (int k = 0; k < C; k++) { q[k] = (t * C + k < P.ni) ? 1.0 : 0.0; phi[k] = 0.0; }
-    double XL = (t > 0 && t * C - 1 < P.ni) ? 1.0 : 0.0;                       // value at the left separator
+    double XL = (t > 0 && t * C - 1 < P.ni) ? 1.0 : 0.0;   // value at the left separator
     double qn = ((t + 1) * C < P.ni) ? 1.0 : 0.0;          // first node of the next chunk
     double *hb = P.hist + (size_t)(P.store_full ? p : blockIdx.x) * P.hist_stride;
+    // per-thread view of a slice: C == 1: doubles at [t]; else double2 at [(k/2)*T + t]
+    double *hw = hb + ((C == 1) ? t : 2 * t);               // write cursor (slice j)
+    const double *hr = hw + (size_t)n * SL;                 // read cursor (slice n-j)
+    auto store_slice = [&](double *dst) {
+      if constexpr (C == 1) dst[0] = q[0];
+      else {
 #pragma unroll
-    for (int k = 0; k < C; k++) hb[(size_t)k * T + t] = q[k];
+        for (int k = 0; k < C; k += 2) *reinterpret_cast<double2 *>(dst + k * T) = make_double2(q[k], q[k + 1]);
+      }
+    };
+    store_slice(hw);
+    const double *wq = P.w;
+    const bool full = P.store_full != 0;
 
     // ------------------------------------------------------------------ the contour march
-    for (int j = 1; j <= n; j++) {
-      const bool pairing = (2 * j > n);
-      double qo[C];
-      if (pairing) {
-        const double *hs = hb + (size_t)(n - j) * SL;
+    auto prefetch = [&](int jj, const double *src) {   // slice n-jj -> s_qo[jj&1]
+      if (STAGE && 2 * jj > n && jj <= n) {
+        if constexpr (C == 1) cp_async8(&s_qo[jj & 1][0][t][0], src);
+        else {
 #pragma unroll
-        for (int k = 0; k < C; k++) qo[k] = hs[(size_t)k * T + t];
+          for (int k = 0; k < C; k += 2) cp_async16(&s_qo[jj & 1][k / 2][t][0], src + k * T);
+        }
       }
-      // right-hand side b = A q (pre-scaled by the pivots on chunk nodes), level-1 solve
+      if (STAGE) cp_async_commit();
+    };
+    prefetch(1, hr - SL);
+    for (int j = 1; j <= n; j++) {
+      hw += SL; hr -= SL;
+      const bool pairing = (2 * j > n);
+      prefetch(j + 1, hr - SL);   // the slice the NEXT step pairs with; written >= 1 step ago by this thread
+      // right-hand side b = A q and the level-1 (chunk) solve with zero separators
       double z[CA];
       double zlast = 0.0, z0 = 0.0;
       if constexpr (CI > 0) {
+        if constexpr (UNI) {
+          // b_k = A_off (q_{k-1} + q_{k+1} + 4 q_k); u = forward sweep of b/A_off; z_k = ca_k u_k - be_k z_{k+1}
 #pragma unroll
-        for (int k = 0; k < CI; k++) {
-          double qm = (k == 0) ? XL : q[k - 1], qp = q[k + 1];
-          double bk = UNI ? fma(ca[k], qm + qp, cd[k] * q[k]) : fma(ca[k], qm, fma(cu[k], qp, cd[k] * q[k]));
-          z[k] = (k == 0) ? bk : fma(-al[k], z[k - 1], bk);
+          for (int k = 0; k < CI; k++) {
+            double qm = (k == 0) ? XL : q[k - 1], qp = q[k + 1];
+            double tk = fma(4.0, q[k], qm + qp);
+            z[k] = (k == 0) ? tk : fma(-al[k], z[k - 1], tk);
+          }
+          z[CI - 1] = ca[CI - 1] * z[CI - 1];
+#pragma unroll
+          for (int k = CI - 2; k >= 0; k--) z[k] = fma(-be[k], z[k + 1], ca[k] * z[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < CI; k++) {
+            double qm = (k == 0) ? XL : q[k - 1], qp = q[k + 1];
+            double bk = fma(ca[k], qm, fma(cu[k], qp, cd[k] * q[k]));
+            z[k] = (k == 0) ? bk : fma(-al[k], z[k - 1], bk);
+          }
+#pragma unroll
+          for (int k = CI - 2; k >= 0; k--) z[k] = fma(-be[k], z[k + 1], z[k]);
         }
-#pragma unroll
-        for (int k = CI - 2; k >= 0; k--) z[k] = fma(-be[k], z[k + 1], z[k]);
         zlast = z[CI - 1]; z0 = z[0];
       }
       const double qprev = (CI > 0) ? q[CI > 0 ? CI - 1 : 0] : XL;
       double r = fma(sAl, qprev, sAd * q[C - 1]);
       if constexpr (CI > 0) r = fma(-sl, zlast, r);
-      double rsep = r;                                    // lane 31: without next-warp terms
+      const double rsep = r;                              // lane 31: without next-warp terms
       {
-        double zfn = shfl_dn_d(z0, 1);
         r = fma(sAu, qn, r);
-        if constexpr (CI > 0) r = fma(-su, zfn, r);
+        if constexpr (CI > 0) { double zfn = shfl_dn_d(z0, 1); r = fma(-su, zfn, r); }
       }
-      if (lane == 31) r = 0.0;
+      r = (lane == 31) ? 0.0 : r;
       // level 2
-      double Z;
-      {
 #pragma unroll
-        for (int s = 0; s < 5; s++) {
-          const int d = 1 << s;
-          double rm = shfl_up_d(r, d), rp = shfl_dn_d(r, d);
-          r = fma(pa_[s], rm, fma(pg_[s], rp, r));
-        }
-        Z = r * binv;
+      for (int s = 0; s < 5; s++) {
+        const int d = 1 << s;
+        double rm = shfl_up_d(r, d), rp = shfl_dn_d(r, d);
+        r = fma(pa_[s], rm, fma(pg_[s], rp, r));
       }
+      const double Z = r * binv;
       // level 3: publish, one barrier, redundant tiny solve
-      double *pb = pub + (j & 1) * nw * PUB + wid * PUB;
-      if (lane == 0) { pb[0] = q[0]; pb[1] = z0; pb[2] = Z; }
-      if (lane == 30) pb[3] = Z;
-      if (lane == 31) pb[4] = rsep;
-      __syncthreads();
+      double (*pb)[PUB] = s_pub[j & 1];
+      if (lane == 0) { *reinterpret_cast<double2 *>(&pb[wid][0]) = make_double2(q[0], z0); pb[wid][2] = Z; }
+      if (lane == 30) pb[wid][3] = Z;
+      if (lane == 31) pb[wid][4] = rsep;
+      if constexpr (NW > 1) __syncthreads(); else __syncwarp();
       double Wm = 0.0, Ww = 0.0;
-      {
-        const double *pp = pub + (j & 1) * nw * PUB;
-        for (int v = 0; v < nw; v++) {
-          double R = pp[v * PUB + 4] - l3[0 * nw + v] * pp[v * PUB + 3];
-          if (v + 1 < nw) {
-            const double *pn = pp + (v + 1) * PUB;
-            R = fma(l3[7 * nw + v], pn[0], R);
-            R = fma(-l3[8 * nw + v], pn[1], R);
-            R = fma(-l3[2 * nw + v], pn[2], R);
-          }
-          Ww = fma(Minv[wid * nw + v], R, Ww);
-          if (wid > 0) Wm = fma(Minv[(wid - 1) * nw + v], R, Wm);
+#pragma unroll
+      for (int v = 0; v < NW; v++) {
+        const double2 p23 = *reinterpret_cast<const double2 *>(&pb[v][2]);   // Z0, Z30
+        const double2 l01 = *reinterpret_cast<const double2 *>(&s_l3[v][0]); // P, cAu
+        double R = fma(-l01.x, p23.y, pb[v][4]);
+        if (v + 1 < NW) {
+          const double2 n01 = *reinterpret_cast<const double2 *>(&pb[(v + 1) % NW][0]);  // qf, zf
+          const double2 l23 = *reinterpret_cast<const double2 *>(&s_l3[v][2]);           // csu, Nx
+          R = fma(l01.y, n01.x, R);
+          R = fma(-l23.x, n01.y, R);
+          R = fma(-l23.y, pb[(v + 1) % NW][2], R);
         }
+        Ww = fma(s_minv[wid][v], R, Ww);
+        if (NW > 1) Wm = fma(s_minv[(wid + NW - 1) % NW][v], R, Wm);
       }
-      double X = (lane == 31) ? Ww : fma(-GL, Wm, fma(-GR, Ww, Z));
+      if (wid == 0) Wm = 0.0;
+      const double X = (lane == 31) ? Ww : fma(-GL, Wm, fma(-GR, Ww, Z));
       double XLn = shfl_up_d(X, 1);
-      if (lane == 0) XLn = Wm;
+      XLn = (lane == 0) ? Wm : XLn;
       // level-1 correction
       if constexpr (CI > 0) {
 #pragma unroll
@@ -347,21 +392,27 @@ __global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
       q[C - 1] = X;
       XL = XLn;
       qn = shfl_dn_d(q[0], 1);
-      if (lane == 31) qn = 0.0;   // supplied through the publish buffer
+      qn = (lane == 31) ? 0.0 : qn;   // supplied through the publish buffer
       // history + fused quadrature
-      if (P.store_full || 2 * j < n) {
-        double *hs = hb + (size_t)j * SL;
+      if (full || 2 * j < n) store_slice(hw);
+      if (2 * j >= n) {
+        const double wj = __ldg(wq + j);   // j > n/2: 2*w_j (pair j, n-j); j == n/2: w_j
+        if (pairing) {
+          if (STAGE) cp_async_wait1();   // everything but the newest group (step j+1) has landed
+          if constexpr (C == 1) phi[0] = fma(wj * q[0], STAGE ? s_qo[j & 1][0][t][0] : hr[0], phi[0]);
+          else {
 #pragma unroll
-        for (int k = 0; k < C; k++) hs[(size_t)k * T + t] = q[k];
-      }
-      if (pairing) {
-        const double w2 = 2.0 * __ldg(P.w + j);
+            for (int k = 0; k < C; k += 2) {
+              const double2 v = STAGE ? *reinterpret_cast<const double2 *>(&s_qo[j & 1][k / 2][t][0])
+                                      : *reinterpret_cast<const double2 *>(hr + k * T);
+              phi[k] = fma(wj * q[k], v.x, phi[k]);
+              phi[k + 1] = fma(wj * q[k + 1], v.y, phi[k + 1]);
+            }
+          }
+        } else {
 #pragma unroll
-        for (int k = 0; k < C; k++) phi[k] = fma(w2 * q[k], qo[k], phi[k]);
-      } else if (2 * j == n) {
-        const double w1 = __ldg(P.w + j);
-#pragma unroll
-        for (int k = 0; k < C; k++) phi[k] = fma(w1 * q[k], q[k], phi[k]);
+          for (int k = 0; k < C; k++) phi[k] = fma(wj * q[k], q[k], phi[k]);
+        }
       }
     }
 
@@ -375,10 +426,10 @@ __global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
         const double f0 = P.f0[(size_t)p * P.N + i];
         P.out[(size_t)p * P.out_stride + g] = P.sign * (f0 - phi[k]);
         P.phi[(size_t)p * P.N + i] = phi[k];
-        double hw;
-        if (P.uniform) hw = L / (P.N - 1);
-        else { const double *x = P.x + (size_t)p * P.N; hw = 0.5 * ((x[i] - x[i - 1]) + (x[i + 1] - x[i])); }
-        qsum += (P.uniform ? 0.5 * (hw + hw) : hw) * q[k];
+        double hw2;
+        if (P.uniform) { double h = L / (P.N - 1); hw2 = 0.5 * (h + h); }
+        else { const double *x = P.x + (size_t)p * P.N; hw2 = 0.5 * ((x[i] - x[i - 1]) + (x[i + 1] - x[i])); }
+        qsum += hw2 * q[k];
         if (P.eta_full) P.eta_full[(size_t)p * P.N + i] = P.eta_mid[(size_t)p * P.eta_stride + g];
       }
     }
@@ -391,11 +442,11 @@ __global__ void __launch_bounds__(TMAX, MINB) march_ie_kernel(MarchParams P) {
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, d);
-    if (lane == 0) red[wid] = qsum;
+    if (lane == 0) s_red[wid] = qsum;
     __syncthreads();
     if (t == 0) {
       double s = 0.0;
-      for (int w = 0; w < nw; w++) s += red[w];
+      for (int w = 0; w < NW; w++) s += s_red[w];
       double len = P.uniform ? L : (P.x[(size_t)p * P.N + P.N - 1] - P.x[(size_t)p * P.N]);
       P.Q[p] = s / len;
     }
