@@ -131,6 +131,9 @@ typedef struct scftb_mixer scftb_mixer;
 int scftb_mixer_create(scftb_engine *e, int nprob, double tol, double lmd, int nn, int Final, scftb_mixer **out);
 int scftb_mixer_destroy(scftb_mixer *m);
 int scftb_mixer_reset(scftb_mixer *m, const double *x, int x_is_device, void *stream);
+/* freeze = 1 (default): converged / NaN problems are skipped from then on, as adm_chen returns or
+ * exits for them; 0: every problem is evaluated in every iteration (fixed-iteration benchmarks). */
+int scftb_mixer_set_freeze(scftb_mixer *m, int freeze);
 int scftb_mixer_iterate_device(scftb_mixer *m, void *stream);
 /* done[p]: 0 running, 1 converged, 2 NaN; iters[p]: iteration index at which it stopped; err[p]: last max|F| */
 int scftb_mixer_status(scftb_mixer *m, void *stream, int *done, int *iters, double *err);

@@ -58,13 +58,23 @@ __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_
 __device__ __forceinline__ double shfl_dn_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double shfl_d(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
 
+// shared-memory accesses through precomputed 32-bit shared-window addresses: keeps the per-step
+// address arithmetic out of the contour loop
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts128(unsigned a, double v0, double v1) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v0), "d"(v1) : "memory");
+}
+__device__ __forceinline__ double lds64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ double2 lds128(unsigned a) {
+  double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory"); return v;
+}
+
 // Ampere-style asynchronous global->shared copies (LDGSTS)
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+__device__ __forceinline__ void cp_async16(unsigned sa, const void *gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+__device__ __forceinline__ void cp_async8(unsigned sa, const void *gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
@@ -132,7 +142,7 @@ __host__ __device__ inline int hist_index(int C, int T, int t, int k) {
   return (C == 1) ? t : ((k >> 1) * T + t) * 2 + (k & 1);
 }
 
-constexpr int PUB = 8;  // doubles per warp in a publish buffer: qf, zf, Z0, Z30, rsep
+constexpr int PUB = 8;  // doubles per warp in a publish buffer: [0] qf, [1] zf, [2] Z0 (lane 0); [4] Z30 (lane 30), [5] rsep (lane 31)
 
 template <int C, int T, bool UNI, int MINB>
 __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
@@ -165,6 +175,9 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     {
       Row rs = assemble_row(P, p, t * C + CI, L, dt);
       sAl = rs.Al; sAd = rs.Ad; sAu = rs.Au; sl = rs.Tl; sd = rs.Td; su = rs.Tu;
+      // UNI: A's separator row is A_off * (1, 4, 1); the Dirichlet zeroing is carried by the neighbour
+      // values (exactly 0 on walls / padding), so one coefficient is kept (in sAd)
+      if (UNI) sAd = (rs.Al != 0.0) ? rs.Al : rs.Au;
     }
     if constexpr (CI > 0) {
       double Tl0 = 0, TuL = 0, pinv_prev = 0, Tu_prev = 0;
@@ -245,7 +258,8 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     const double GL = pcr(A0), GR = pcr(C30);
     // ------------------------------------------------------------------ level 3 setup
     if (lane == 31) {
-      s_l3[wid][0] = l3P; s_l3[wid][1] = sAu; s_l3[wid][2] = (CI > 0) ? su : 0.0; s_l3[wid][3] = l3N;
+      s_l3[wid][0] = l3P; s_l3[wid][1] = (wid + 1 < NW) ? (UNI ? sAd : sAu) : 0.0;
+      s_l3[wid][2] = (CI > 0) ? su : 0.0; s_l3[wid][3] = l3N;
       s_l3s[wid][0] = l3D;
     }
     if (lane == 0) { s_l3s[wid][1] = GL; s_l3s[wid][2] = GR; }
@@ -299,12 +313,22 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     const bool full = P.store_full != 0;
 
     // ------------------------------------------------------------------ the contour march
-    auto prefetch = [&](int jj, const double *src) {   // slice n-jj -> s_qo[jj&1]
+    // shared-window addresses and the lane's share of the level-3 solve (loop invariants)
+    constexpr unsigned QO_BUF = (unsigned)(((C + 1) / 2) * T * 16);   // bytes per staging buffer
+    constexpr unsigned PUB_BUF = (unsigned)(NW * PUB * 8);
+    const unsigned qo_me = smem_u32(&s_qo[0][0][STAGE ? t : 0][0]);
+    const unsigned pub_me = smem_u32(&s_pub[0][wid][0]);
+    const int v3 = lane & (NW - 1);                // this lane evaluates separator row v3 of level 3
+    const unsigned pub_v = smem_u32(&s_pub[0][v3][0]), pub_vn = smem_u32(&s_pub[0][(v3 + 1) % NW][0]);
+    const double c3P = s_l3[v3][0], c3Au = s_l3[v3][1], c3su = s_l3[v3][2], c3Nx = s_l3[v3][3];
+    const double mW = s_minv[wid][v3], mM = (wid > 0) ? s_minv[(wid + NW - 1) % NW][v3] : 0.0;
+    auto prefetch = [&](int jj, const double *src) {   // slice n-jj -> staging buffer jj&1
       if (STAGE && 2 * jj > n && jj <= n) {
-        if constexpr (C == 1) cp_async8(&s_qo[jj & 1][0][t][0], src);
+        const unsigned dst = qo_me + (jj & 1) * QO_BUF;
+        if constexpr (C == 1) cp_async8(dst, src);
         else {
 #pragma unroll
-          for (int k = 0; k < C; k += 2) cp_async16(&s_qo[jj & 1][k / 2][t][0], src + k * T);
+          for (int k = 0; k < C; k += 2) cp_async16(dst + (k / 2) * T * 16, src + k * T);
         }
       }
       if (STAGE) cp_async_commit();
@@ -342,11 +366,11 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
         zlast = z[CI - 1]; z0 = z[0];
       }
       const double qprev = (CI > 0) ? q[CI > 0 ? CI - 1 : 0] : XL;
-      double r = fma(sAl, qprev, sAd * q[C - 1]);
+      double r = UNI ? sAd * fma(4.0, q[C - 1], qprev) : fma(sAl, qprev, sAd * q[C - 1]);   // UNI: sAd holds A_off
       if constexpr (CI > 0) r = fma(-sl, zlast, r);
       const double rsep = r;                              // lane 31: without next-warp terms
       {
-        r = fma(sAu, qn, r);
+        r = fma(UNI ? sAd : sAu, qn, r);
         if constexpr (CI > 0) { double zfn = shfl_dn_d(z0, 1); r = fma(-su, zfn, r); }
       }
       r = (lane == 31) ? 0.0 : r;
@@ -358,29 +382,29 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
         r = fma(pa_[s], rm, fma(pg_[s], rp, r));
       }
       const double Z = r * binv;
-      // level 3: publish, one barrier, redundant tiny solve
-      double (*pb)[PUB] = s_pub[j & 1];
-      if (lane == 0) { *reinterpret_cast<double2 *>(&pb[wid][0]) = make_double2(q[0], z0); pb[wid][2] = Z; }
-      if (lane == 30) pb[wid][3] = Z;
-      if (lane == 31) pb[wid][4] = rsep;
+      // level 3: publish, one barrier, then every group of NW lanes solves the warp-separator system
+      // cooperatively (lane v3 forms R_v3, butterfly sum over the group) -> every lane holds W_wid, W_wid-1
+      const unsigned pbuf = (j & 1) * PUB_BUF;
+      if (lane == 0) { sts128(pub_me + pbuf, q[0], z0); sts64(pub_me + pbuf + 16, Z); }
+      if (lane == 30) sts64(pub_me + pbuf + 32, Z);
+      if (lane == 31) sts64(pub_me + pbuf + 40, rsep);
       if constexpr (NW > 1) __syncthreads(); else __syncwarp();
-      double Wm = 0.0, Ww = 0.0;
+      double Ww, Wm;
+      {
+        const double2 own = lds128(pub_v + pbuf + 32);     // Z30_v, rsep_v
+        const double2 nxt = lds128(pub_vn + pbuf);         // qf_{v+1}, zf_{v+1}
+        const double z0n = lds64(pub_vn + pbuf + 16);      // Z0_{v+1}
+        double R = fma(-c3P, own.x, own.y);
+        double R2 = fma(c3Au, nxt.x, -c3su * nxt.y);
+        R2 = fma(-c3Nx, z0n, R2);
+        R += R2;
+        Ww = mW * R; Wm = mM * R;
 #pragma unroll
-      for (int v = 0; v < NW; v++) {
-        const double2 p23 = *reinterpret_cast<const double2 *>(&pb[v][2]);   // Z0, Z30
-        const double2 l01 = *reinterpret_cast<const double2 *>(&s_l3[v][0]); // P, cAu
-        double R = fma(-l01.x, p23.y, pb[v][4]);
-        if (v + 1 < NW) {
-          const double2 n01 = *reinterpret_cast<const double2 *>(&pb[(v + 1) % NW][0]);  // qf, zf
-          const double2 l23 = *reinterpret_cast<const double2 *>(&s_l3[v][2]);           // csu, Nx
-          R = fma(l01.y, n01.x, R);
-          R = fma(-l23.x, n01.y, R);
-          R = fma(-l23.y, pb[(v + 1) % NW][2], R);
+        for (int d = 1; d < NW; d <<= 1) {
+          Ww += __shfl_xor_sync(0xffffffffu, Ww, d);
+          Wm += __shfl_xor_sync(0xffffffffu, Wm, d);
         }
-        Ww = fma(s_minv[wid][v], R, Ww);
-        if (NW > 1) Wm = fma(s_minv[(wid + NW - 1) % NW][v], R, Wm);
       }
-      if (wid == 0) Wm = 0.0;
       const double X = (lane == 31) ? Ww : fma(-GL, Wm, fma(-GR, Ww, Z));
       double XLn = shfl_up_d(X, 1);
       XLn = (lane == 0) ? Wm : XLn;
@@ -399,12 +423,12 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
         const double wj = __ldg(wq + j);   // j > n/2: 2*w_j (pair j, n-j); j == n/2: w_j
         if (pairing) {
           if (STAGE) cp_async_wait1();   // everything but the newest group (step j+1) has landed
-          if constexpr (C == 1) phi[0] = fma(wj * q[0], STAGE ? s_qo[j & 1][0][t][0] : hr[0], phi[0]);
+          const unsigned src = qo_me + (j & 1) * QO_BUF;
+          if constexpr (C == 1) phi[0] = fma(wj * q[0], STAGE ? lds64(src) : hr[0], phi[0]);
           else {
 #pragma unroll
             for (int k = 0; k < C; k += 2) {
-              const double2 v = STAGE ? *reinterpret_cast<const double2 *>(&s_qo[j & 1][k / 2][t][0])
-                                      : *reinterpret_cast<const double2 *>(hr + k * T);
+              const double2 v = STAGE ? lds128(src + (k / 2) * T * 16) : *reinterpret_cast<const double2 *>(hr + k * T);
               phi[k] = fma(wj * q[k], v.x, phi[k]);
               phi[k + 1] = fma(wj * q[k + 1], v.y, phi[k + 1]);
             }

@@ -28,7 +28,7 @@ constexpr int AND_EPT = 6;    // entries of (U,V) per thread: nn <= 50 -> 50*51/
 constexpr int AND_NN_MAX = 50;
 
 struct AndersonParams {
-  int n, nprob, R, nm, k, Final;
+  int n, nprob, R, nm, k, Final, freeze;
   double tol, lmd;
   double *X, *Y;       // [nprob][R][n]
   double *xfinal;      // [nprob][n]
@@ -38,7 +38,7 @@ struct AndersonParams {
 
 __global__ void __launch_bounds__(AND_THREADS) anderson_kernel(AndersonParams A) {
   const int p = blockIdx.x, tid = threadIdx.x, n = A.n, R = A.R, k = A.k;
-  if (A.done[p]) return;
+  if (A.freeze && A.done[p]) return;
   extern __shared__ double sm[];
   const int nm = A.nm;
   double *U = sm;                          // [nm][nm]
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(AND_THREADS) anderson_kernel(AndersonParams A)
   double *red = D + (nm + 1) * (AND_TILE + 1);   // [AND_THREADS]
   int *ired = (int *)(red + AND_THREADS);         // [AND_THREADS]
   int *ipiv = ired + AND_THREADS;                 // [nm]
-  __shared__ int s_irow, s_icol, s_sing, s_m;
+  __shared__ int s_irow, s_icol, s_sing;
   __shared__ double s_pivinv;
 
   const double *Xp = A.X + (size_t)p * R * n, *Yp = A.Y + (size_t)p * R * n;
@@ -72,7 +72,10 @@ __global__ void __launch_bounds__(AND_THREADS) anderson_kernel(AndersonParams A)
   bad = ired[0];
   __syncthreads();
   if (tid == 0) A.err[p] = bad ? nan("") : err;
-  if (bad) { if (tid == 0) { A.done[p] = 2; A.iters[p] = k; } return; }
+  if (bad) {   // the reference exit(1)s here; frozen unless the caller asked to keep evaluating (benchmarks)
+    if (tid == 0 && A.done[p] == 0) { A.done[p] = 2; A.iters[p] = k; }
+    if (A.freeze) return;
+  }
   if (err < A.tol) {                       // converged: x_old = X[k] (ADM_chen_C.c:71-84)
     for (int i = tid; i < n; i += AND_THREADS) A.xfinal[(size_t)p * n + i] = Xk[i];
     if (tid == 0) { A.done[p] = 1; A.iters[p] = k; }
@@ -217,7 +220,7 @@ using namespace scftb;
 
 struct scftb_mixer {
   scftb_engine *e;
-  int nprob, nn, nm, R, Final, k;
+  int nprob, nn, nm, R, Final, k, freeze;
   double lmd, tol;
   double *X, *Y, *xfinal, *lk, *err;
   int *k_restart, *done, *iters;
@@ -241,7 +244,7 @@ int scftb_mixer_create(scftb_engine *e, int nprob, double tol, double lmd, int n
   if (nn < 0 || nn > AND_NN_MAX) return fail(SCFTB_ERR_ARG, "mixer: mixing window nn must be in [0, 50]");
   scftb_mixer *m = new scftb_mixer();
   m->e = e; m->nprob = nprob; m->nn = nn; m->nm = std::min(nn, e->ni); m->R = m->nm + 2;
-  m->Final = Final; m->k = 0; m->lmd = lmd; m->tol = tol;
+  m->Final = Final; m->k = 0; m->lmd = lmd; m->tol = tol; m->freeze = 1;
   m->X = m->Y = m->xfinal = m->lk = m->err = nullptr; m->k_restart = m->done = m->iters = nullptr;
   const size_t n = e->ni, ring = (size_t)nprob * m->R * n;
   CK(cudaSetDevice(e->cfg.device));
@@ -258,6 +261,12 @@ int scftb_mixer_create(scftb_engine *e, int nprob, double tol, double lmd, int n
             sizeof(int) * (AND_THREADS + m->nm + 4);
   CKM(cudaFuncSetAttribute((const void *)anderson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
   *out = m;
+  return SCFTB_OK;
+}
+
+int scftb_mixer_set_freeze(scftb_mixer *m, int freeze) {
+  if (!m) return fail(SCFTB_ERR_ARG, "mixer: null argument");
+  m->freeze = freeze != 0;
   return SCFTB_OK;
 }
 
@@ -293,11 +302,11 @@ int scftb_mixer_iterate_device(scftb_mixer *m, void *stream) {
   }
   const long long stride = (long long)m->R * e->ni;
   const size_t slot = (size_t)(m->k % m->R) * e->ni;
-  int rc = launch_march(e, m->nprob, m->X + slot, stride, m->Y + slot, stride, m->done, st);
+  int rc = launch_march(e, m->nprob, m->X + slot, stride, m->Y + slot, stride, m->freeze ? m->done : nullptr, st);
   if (rc) return rc;
   AndersonParams A;
   A.n = e->ni; A.nprob = m->nprob; A.R = m->R; A.nm = m->nm; A.k = m->k; A.Final = m->Final;
-  A.tol = m->tol; A.lmd = m->lmd;
+  A.tol = m->tol; A.lmd = m->lmd; A.freeze = m->freeze;
   A.X = m->X; A.Y = m->Y; A.xfinal = m->xfinal; A.lk = m->lk; A.err = m->err;
   A.k_restart = m->k_restart; A.done = m->done; A.iters = m->iters;
   anderson_kernel<<<m->nprob, AND_THREADS, m->smem, st>>>(A);

@@ -39,7 +39,7 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_bind_global", "scftb_callback_nr1", "scftb_callback_c0", "scftb_callback_fixedpoint_c0",
            "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_adm_chen_batch",
            "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
-           "scftb_mixer_status", "scftb_mixer_get_x", "scftb_set_timing", "scftb_get_march_ms"]
+           "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms"]
 
 
 def lib():
@@ -75,6 +75,7 @@ def lib():
         L.scftb_mixer_destroy.argtypes = [C.c_void_p]
         L.scftb_mixer_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.scftb_mixer_iterate_device.argtypes = [C.c_void_p, C.c_void_p]
+        L.scftb_mixer_set_freeze.argtypes = [C.c_void_p, C.c_int]
         L.scftb_mixer_status.argtypes = [C.c_void_p, C.c_void_p, _ip, _ip, _dp]
         L.scftb_mixer_get_x.argtypes = [C.c_void_p, C.c_void_p, _dp]
         L.scftb_set_timing.argtypes = [C.c_void_p, C.c_int]
@@ -200,6 +201,9 @@ class AndersonBatch:
             self._h = None
 
     __del__ = close
+
+    def set_freeze(self, freeze):
+        _chk(lib().scftb_mixer_set_freeze(self._h, int(freeze)))
 
     def reset(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
