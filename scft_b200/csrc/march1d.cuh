@@ -144,7 +144,7 @@ __host__ __device__ inline int hist_index(int C, int T, int t, int k) {
 
 constexpr int PUB = 8;  // doubles per warp in a publish buffer: [0] qf, [1] zf, [2] Z0 (lane 0); [4] Z30 (lane 30), [5] rsep (lane 31)
 
-template <int C, int T, bool UNI, int MINB>
+template <int C, int T, bool UNI, int MINB, bool S2S>
 __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
   static_assert(C == 1 || (C % 2) == 0, "C must be 1 or even");
   constexpr int CI = C - 1;             // chunk-interior nodes per thread
@@ -162,6 +162,11 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
   // own 16-byte pieces, so no barrier is involved
   constexpr bool STAGE = (C * T <= 2048);   // 32 KB of static shared memory at most
   __shared__ __align__(16) double s_qo[STAGE ? 2 : 1][STAGE ? (C + 1) / 2 : 1][STAGE ? T : 1][2];
+  // S2S ("state to shared"): the phi accumulators and the cyclic-reduction multipliers live in shared
+  // memory instead of registers, buying one more resident CTA per SM for the wide-chunk variants
+  __shared__ __align__(16) double s_phi[S2S ? (C + 1) / 2 : 1][S2S ? T : 1][2];
+  __shared__ __align__(16) double s_pcr[S2S ? 5 : 1][S2S ? T : 1][2];
+  __shared__ __align__(16) double s_lane[S2S ? 5 : 1][S2S ? T : 1][2];   // per-lane level-2/3 constants
   const int n = P.nsteps;
   const double dt = 1.0 / n;            // time_step = 1/(total_time_step-1), scft.cc:29
 
@@ -244,6 +249,7 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
       a = alpha * am;
       c = gamma * cp;
       pa_[s] = alpha; pg_[s] = gamma;
+      if constexpr (S2S) { s_pcr[s][t][0] = alpha; s_pcr[s][t][1] = gamma; }
     }
     const double binv = 1.0 / b;
     auto pcr = [&](double r) {
@@ -295,6 +301,10 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     double q[C], phi[C];
 #pragma unroll
     for (int k = 0; k < C; k++) { q[k] = (t * C + k < P.ni) ? 1.0 : 0.0; phi[k] = 0.0; }
+    if constexpr (S2S) {
+#pragma unroll
+      for (int k = 0; k < C; k += 2) { s_phi[k / 2][t][0] = 0.0; s_phi[k / 2][t][1] = 0.0; }
+    }
     double XL = (t > 0 && t * C - 1 < P.ni) ? 1.0 : 0.0;   // value at the left separator
     double qn = ((t + 1) * C < P.ni) ? 1.0 : 0.0;          // first node of the next chunk
     double *hb = P.hist + (size_t)(P.store_full ? p : blockIdx.x) * P.hist_stride;
@@ -318,10 +328,16 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     constexpr unsigned PUB_BUF = (unsigned)(NW * PUB * 8);
     const unsigned qo_me = smem_u32(&s_qo[0][0][STAGE ? t : 0][0]);
     const unsigned pub_me = smem_u32(&s_pub[0][wid][0]);
+    const unsigned phi_me = smem_u32(&s_phi[0][S2S ? t : 0][0]), pcr_me = smem_u32(&s_pcr[0][S2S ? t : 0][0]);
     const int v3 = lane & (NW - 1);                // this lane evaluates separator row v3 of level 3
     const unsigned pub_v = smem_u32(&s_pub[0][v3][0]), pub_vn = smem_u32(&s_pub[0][(v3 + 1) % NW][0]);
-    const double c3P = s_l3[v3][0], c3Au = s_l3[v3][1], c3su = s_l3[v3][2], c3Nx = s_l3[v3][3];
-    const double mW = s_minv[wid][v3], mM = (wid > 0) ? s_minv[(wid + NW - 1) % NW][v3] : 0.0;
+    double c3P = s_l3[v3][0], c3Au = s_l3[v3][1], c3su = s_l3[v3][2], c3Nx = s_l3[v3][3];
+    double mW = s_minv[wid][v3], mM = (wid > 0) ? s_minv[(wid + NW - 1) % NW][v3] : 0.0;
+    const unsigned lane_me = smem_u32(&s_lane[0][S2S ? t : 0][0]);
+    if constexpr (S2S) {
+      sts128(lane_me, c3P, c3Au); sts128(lane_me + T * 16, c3su, c3Nx); sts128(lane_me + 2 * T * 16, mW, mM);
+      sts128(lane_me + 3 * T * 16, GL, GR); sts128(lane_me + 4 * T * 16, binv, 0.0);
+    }
     auto prefetch = [&](int jj, const double *src) {   // slice n-jj -> staging buffer jj&1
       if (STAGE && 2 * jj > n && jj <= n) {
         const unsigned dst = qo_me + (jj & 1) * QO_BUF;
@@ -379,21 +395,29 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
       for (int s = 0; s < 5; s++) {
         const int d = 1 << s;
         double rm = shfl_up_d(r, d), rp = shfl_dn_d(r, d);
-        r = fma(pa_[s], rm, fma(pg_[s], rp, r));
+        if constexpr (S2S) { const double2 ag = lds128(pcr_me + s * T * 16); r = fma(ag.x, rm, fma(ag.y, rp, r)); }
+        else r = fma(pa_[s], rm, fma(pg_[s], rp, r));
       }
-      const double Z = r * binv;
+      const double Z = r * (S2S ? lds64(lane_me + 4 * T * 16) : binv);
       // level 3: publish, one barrier, then every group of NW lanes solves the warp-separator system
       // cooperatively (lane v3 forms R_v3, butterfly sum over the group) -> every lane holds W_wid, W_wid-1
       const unsigned pbuf = (j & 1) * PUB_BUF;
-      if (lane == 0) { sts128(pub_me + pbuf, q[0], z0); sts64(pub_me + pbuf + 16, Z); }
-      if (lane == 30) sts64(pub_me + pbuf + 32, Z);
-      if (lane == 31) sts64(pub_me + pbuf + 40, rsep);
+      asm volatile(
+          "{\n .reg .pred p0, p30, p31;\n"
+          " setp.eq.s32 p0, %0, 0;\n setp.eq.s32 p30, %0, 30;\n setp.eq.s32 p31, %0, 31;\n"
+          " @p0 st.shared.v2.f64 [%1], {%2, %3};\n @p0 st.shared.f64 [%1+16], %4;\n"
+          " @p30 st.shared.f64 [%1+32], %4;\n @p31 st.shared.f64 [%1+40], %5;\n}"
+          ::"r"(lane), "r"(pub_me + pbuf), "d"(q[0]), "d"(z0), "d"(Z), "d"(rsep) : "memory");
       if constexpr (NW > 1) __syncthreads(); else __syncwarp();
       double Ww, Wm;
       {
         const double2 own = lds128(pub_v + pbuf + 32);     // Z30_v, rsep_v
         const double2 nxt = lds128(pub_vn + pbuf);         // qf_{v+1}, zf_{v+1}
         const double z0n = lds64(pub_vn + pbuf + 16);      // Z0_{v+1}
+        if constexpr (S2S) {
+          const double2 c01 = lds128(lane_me), c23 = lds128(lane_me + T * 16), mm = lds128(lane_me + 2 * T * 16);
+          c3P = c01.x; c3Au = c01.y; c3su = c23.x; c3Nx = c23.y; mW = mm.x; mM = mm.y;
+        }
         double R = fma(-c3P, own.x, own.y);
         double R2 = fma(c3Au, nxt.x, -c3su * nxt.y);
         R2 = fma(-c3Nx, z0n, R2);
@@ -405,7 +429,9 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
           Wm += __shfl_xor_sync(0xffffffffu, Wm, d);
         }
       }
-      const double X = (lane == 31) ? Ww : fma(-GL, Wm, fma(-GR, Ww, Z));
+      double GLs = GL, GRs = GR;
+      if constexpr (S2S) { const double2 g = lds128(lane_me + 3 * T * 16); GLs = g.x; GRs = g.y; }
+      const double X = (lane == 31) ? Ww : fma(-GLs, Wm, fma(-GRs, Ww, Z));
       double XLn = shfl_up_d(X, 1);
       XLn = (lane == 0) ? Wm : XLn;
       // level-1 correction
@@ -429,18 +455,31 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
 #pragma unroll
             for (int k = 0; k < C; k += 2) {
               const double2 v = STAGE ? lds128(src + (k / 2) * T * 16) : *reinterpret_cast<const double2 *>(hr + k * T);
-              phi[k] = fma(wj * q[k], v.x, phi[k]);
-              phi[k + 1] = fma(wj * q[k + 1], v.y, phi[k + 1]);
+              if constexpr (S2S) {
+                const double2 ph = lds128(phi_me + (k / 2) * T * 16);
+                sts128(phi_me + (k / 2) * T * 16, fma(wj * q[k], v.x, ph.x), fma(wj * q[k + 1], v.y, ph.y));
+              } else {
+                phi[k] = fma(wj * q[k], v.x, phi[k]);
+                phi[k + 1] = fma(wj * q[k + 1], v.y, phi[k + 1]);
+              }
             }
           }
         } else {
 #pragma unroll
           for (int k = 0; k < C; k++) phi[k] = fma(wj * q[k], q[k], phi[k]);
+          if constexpr (S2S) {   // the one unpaired slice (j = n/2) seeds the shared accumulators
+#pragma unroll
+            for (int k = 0; k < C; k += 2) sts128(phi_me + (k / 2) * T * 16, phi[k], phi[k + 1]);
+          }
         }
       }
     }
 
     // ------------------------------------------------------------------ residual, phi, Q
+    if constexpr (S2S) {
+#pragma unroll
+      for (int k = 0; k < C; k += 2) { const double2 ph = lds128(phi_me + (k / 2) * T * 16); phi[k] = ph.x; phi[k + 1] = ph.y; }
+    }
     double qsum = 0.0;
 #pragma unroll
     for (int k = 0; k < C; k++) {
