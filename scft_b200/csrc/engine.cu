@@ -117,9 +117,9 @@ __global__ void spline_bnd_kernel(int nprob, int N, const double *x, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int C, int T, int MINB, bool S2S = false>
+template <int C, int T, int MINB>
 static march_fn pick(bool uni) {
-  return uni ? (march_fn)march_ie_kernel<C, T, true, MINB, S2S> : (march_fn)march_ie_kernel<C, T, false, MINB, S2S>;
+  return uni ? (march_fn)march_ie_kernel<C, T, true, MINB> : (march_fn)march_ie_kernel<C, T, false, MINB>;
 }
 
 // nodes per thread C and threads per problem T for ni interior nodes.  SCFTB_FORCE_C=4 selects the
@@ -139,7 +139,7 @@ int choose_kernel(int ni, bool uni, KernelChoice &kc) {
   if (C == 2 && T == 128) kc.fn = pick<2, 128, 4>(uni);
   if (C == 4 && T == 128) kc.fn = pick<4, 128, 4>(uni);
   if (C == 4 && T == 256) kc.fn = pick<4, 256, 2>(uni);
-  if (C == 8 && T == 128) kc.fn = (getenv("SCFTB_MINB") && atoi(getenv("SCFTB_MINB")) == 4) ? pick<8, 128, 4, true>(uni) : pick<8, 128, 3>(uni);
+  if (C == 8 && T == 128) kc.fn = pick<8, 128, 3>(uni);
   if (C == 16 && T == 128) kc.fn = pick<16, 128, 1>(uni);
   if (C == 16 && T == 256) kc.fn = pick<16, 256, 1>(uni);
   if (!kc.fn) return 1;

@@ -144,7 +144,7 @@ __host__ __device__ inline int hist_index(int C, int T, int t, int k) {
 
 constexpr int PUB = 8;  // doubles per warp in a publish buffer: [0] qf, [1] zf, [2] Z0 (lane 0); [4] Z30 (lane 30), [5] rsep (lane 31)
 
-template <int C, int T, bool UNI, int MINB, bool S2S>
+template <int C, int T, bool UNI, int MINB>
 __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
   static_assert(C == 1 || (C % 2) == 0, "C must be 1 or even");
   constexpr int CI = C - 1;             // chunk-interior nodes per thread
@@ -162,11 +162,6 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
   // own 16-byte pieces, so no barrier is involved
   constexpr bool STAGE = (C * T <= 2048);   // 32 KB of static shared memory at most
   __shared__ __align__(16) double s_qo[STAGE ? 2 : 1][STAGE ? (C + 1) / 2 : 1][STAGE ? T : 1][2];
-  // S2S ("state to shared"): the phi accumulators and the cyclic-reduction multipliers live in shared
-  // memory instead of registers, buying one more resident CTA per SM for the wide-chunk variants
-  __shared__ __align__(16) double s_phi[S2S ? (C + 1) / 2 : 1][S2S ? T : 1][2];
-  __shared__ __align__(16) double s_pcr[S2S ? 5 : 1][S2S ? T : 1][2];
-  __shared__ __align__(16) double s_lane[S2S ? 5 : 1][S2S ? T : 1][2];   // per-lane level-2/3 constants
   const int n = P.nsteps;
   const double dt = 1.0 / n;            // time_step = 1/(total_time_step-1), scft.cc:29
 
@@ -185,36 +180,39 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
       if (UNI) sAd = (rs.Al != 0.0) ? rs.Al : rs.Au;
     }
     if constexpr (CI > 0) {
-      double Tl0 = 0, TuL = 0, pinv_prev = 0, Tu_prev = 0;
-      double alo[CA];                           // pinv_k * Tl_k (setup only)
+      // UL order: eliminate from the chunk's right end towards the left, then substitute left to
+      // right.  z_first is then known after the FIRST sweep (its shuffle to the left neighbour
+      // overlaps the second sweep) and z_last, which the own separator needs, comes out last.
+      double Tl0 = 0, TuL = 0, pinv_next = 0, Tl_next = 0;
+      double ulo[CA];                           // pinv_k * Tu_k (setup only)
 #pragma unroll
-      for (int k = 0; k < CI; k++) {
+      for (int k = CI - 1; k >= 0; k--) {
         Row r = assemble_row(P, p, t * C + k, L, dt);
-        double piv = (k == 0) ? r.Td : r.Td - (r.Tl * pinv_prev) * Tu_prev;
+        double piv = (k == CI - 1) ? r.Td : r.Td - (r.Tu * pinv_next) * Tl_next;
         double pinv = 1.0 / piv;
         // UNI: one off-diagonal coefficient serves both neighbours; the Dirichlet zeroing of A is
         // then carried by the neighbour values themselves (wall / padding nodes are exactly 0),
         // and A's diagonal is 4x the off-diagonal, so no cd[] is kept.
         ca[k] = pinv * ((UNI && r.Al == 0.0) ? r.Au : r.Al); cd[k] = pinv * r.Ad; cu[k] = pinv * r.Au;
-        alo[k] = (k == 0) ? 0.0 : pinv * r.Tl;
-        // UNI: the forward sweep runs on u = y/A_off with the plain Thomas multiplier Tl_k/piv_{k-1}
-        al[k] = (k == 0) ? 0.0 : (UNI ? r.Tl * pinv_prev : alo[k]);
-        be[k] = (k == CI - 1) ? 0.0 : pinv * r.Tu;
+        ulo[k] = (k == CI - 1) ? 0.0 : pinv * r.Tu;
+        // first sweep; UNI runs it on u = y/A_off with the plain multiplier Tu_k/piv_{k+1}
+        al[k] = (k == CI - 1) ? 0.0 : (UNI ? r.Tu * pinv_next : ulo[k]);
+        be[k] = (k == 0) ? 0.0 : pinv * r.Tl;   // second sweep: coupling to node k-1
         if (k == 0) Tl0 = pinv * r.Tl;          // scaled coupling to the left separator
         if (k == CI - 1) TuL = pinv * r.Tu;     // scaled coupling to the own (right) separator
-        pinv_prev = pinv; Tu_prev = r.Tu;
+        pinv_next = pinv; Tl_next = r.Tl;
       }
       // spikes gl = T_loc^-1 (Tl_first e_first), gr = T_loc^-1 (Tu_last e_last)
+      gl[0] = Tl0;
+#pragma unroll
+      for (int k = 1; k < CI; k++) gl[k] = -be[k] * gl[k - 1];
       double y[CA];
-      y[0] = Tl0;
+      y[CI - 1] = TuL;
 #pragma unroll
-      for (int k = 1; k < CI; k++) y[k] = -alo[k] * y[k - 1];
-      gl[CI - 1] = y[CI - 1];
+      for (int k = CI - 2; k >= 0; k--) y[k] = -ulo[k] * y[k + 1];
+      gr[0] = y[0];
 #pragma unroll
-      for (int k = CI - 2; k >= 0; k--) gl[k] = y[k] - be[k] * gl[k + 1];
-      gr[CI - 1] = TuL;
-#pragma unroll
-      for (int k = CI - 2; k >= 0; k--) gr[k] = -be[k] * gr[k + 1];
+      for (int k = 1; k < CI; k++) gr[k] = y[k] - be[k] * gr[k - 1];
     }
     // ------------------------------------------------------------------ Schur rows on separators
     double a, b, c;
@@ -235,9 +233,12 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     if (lane == 31) { a = 0.0; b = 1.0; c = 0.0; }
     if (lane == 0) a = 0.0;
     if (lane == 30) c = 0.0;
-    double pa_[5], pg_[5];
+    // three cyclic-reduction stages (strides 1, 2, 4) leave eight independent 4-unknown systems, one
+    // per residue class lane mod 8; each lane keeps its row of that system's inverse
+    constexpr int NST = 3;
+    double pa_[NST], pg_[NST];
 #pragma unroll
-    for (int s = 0; s < 5; s++) {
+    for (int s = 0; s < NST; s++) {
       const int d = 1 << s;
       double am = shfl_up_d(a, d), bm = shfl_up_d(b, d), cm = shfl_up_d(c, d);
       double ap = shfl_dn_d(a, d), bp = shfl_dn_d(b, d), cp = shfl_dn_d(c, d);
@@ -249,19 +250,43 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
       a = alpha * am;
       c = gamma * cp;
       pa_[s] = alpha; pg_[s] = gamma;
-      if constexpr (S2S) { s_pcr[s][t][0] = alpha; s_pcr[s][t][1] = gamma; }
     }
-    const double binv = 1.0 / b;
+    double inv4[4];
+    {
+      // rows of the class system: lanes g, g+8, g+16, g+24; row m of M^-1 is the solution of M^T x = e_m
+      const int g8 = lane & 7, m8 = lane >> 3;
+      double ra[4], rb[4], rc[4];
+#pragma unroll
+      for (int mm = 0; mm < 4; mm++) { ra[mm] = shfl_d(a, g8 + 8 * mm); rb[mm] = shfl_d(b, g8 + 8 * mm); rc[mm] = shfl_d(c, g8 + 8 * mm); }
+      // M^T is tridiagonal with sub-diagonal rc[i-1] (row i, col i-1), diagonal rb[i], super-diagonal ra[i+1]
+      double cpv[4], dpv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        double lo = (i > 0) ? rc[i - 1] : 0.0, up = (i < 3) ? ra[i + 1] : 0.0, rhs = (i == m8) ? 1.0 : 0.0;
+        double den = rb[i] - lo * ((i > 0) ? cpv[i > 0 ? i - 1 : 0] : 0.0);
+        cpv[i] = up / den;
+        dpv[i] = (rhs - lo * ((i > 0) ? dpv[i > 0 ? i - 1 : 0] : 0.0)) / den;
+      }
+      inv4[3] = dpv[3];
+#pragma unroll
+      for (int i = 2; i >= 0; i--) inv4[i] = dpv[i] - cpv[i] * inv4[i + 1];
+    }
     auto pcr = [&](double r) {
 #pragma unroll
-      for (int s = 0; s < 5; s++) {
+      for (int s = 0; s < NST; s++) {
         const int d = 1 << s;
         double rm = shfl_up_d(r, d), rp = shfl_dn_d(r, d);
         r = fma(pa_[s], rm, fma(pg_[s], rp, r));
       }
-      return r * binv;
+      const int g8 = lane & 7;
+      double r0 = shfl_d(r, g8), r1 = shfl_d(r, g8 + 8), r2 = shfl_d(r, g8 + 16), r3 = shfl_d(r, g8 + 24);
+      return fma(inv4[0], r0, inv4[1] * r1) + fma(inv4[2], r2, inv4[3] * r3);
     };
     const double GL = pcr(A0), GR = pcr(C30);
+    // left neighbour's spikes, so that its separator value can be formed locally (no shuffle on the
+    // critical path); lane 0's left neighbour is the previous warp's separator W_{wid-1} itself
+    double GLm = shfl_up_d(GL, 1), GRm = shfl_up_d(GR, 1);
+    if (lane == 0) { GLm = -1.0; GRm = 0.0; }
     // ------------------------------------------------------------------ level 3 setup
     if (lane == 31) {
       s_l3[wid][0] = l3P; s_l3[wid][1] = (wid + 1 < NW) ? (UNI ? sAd : sAu) : 0.0;
@@ -301,10 +326,6 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     double q[C], phi[C];
 #pragma unroll
     for (int k = 0; k < C; k++) { q[k] = (t * C + k < P.ni) ? 1.0 : 0.0; phi[k] = 0.0; }
-    if constexpr (S2S) {
-#pragma unroll
-      for (int k = 0; k < C; k += 2) { s_phi[k / 2][t][0] = 0.0; s_phi[k / 2][t][1] = 0.0; }
-    }
     double XL = (t > 0 && t * C - 1 < P.ni) ? 1.0 : 0.0;   // value at the left separator
     double qn = ((t + 1) * C < P.ni) ? 1.0 : 0.0;          // first node of the next chunk
     double *hb = P.hist + (size_t)(P.store_full ? p : blockIdx.x) * P.hist_stride;
@@ -322,22 +343,16 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     const double *wq = P.w;
     const bool full = P.store_full != 0;
 
-    // ------------------------------------------------------------------ the contour march
     // shared-window addresses and the lane's share of the level-3 solve (loop invariants)
     constexpr unsigned QO_BUF = (unsigned)(((C + 1) / 2) * T * 16);   // bytes per staging buffer
     constexpr unsigned PUB_BUF = (unsigned)(NW * PUB * 8);
     const unsigned qo_me = smem_u32(&s_qo[0][0][STAGE ? t : 0][0]);
     const unsigned pub_me = smem_u32(&s_pub[0][wid][0]);
-    const unsigned phi_me = smem_u32(&s_phi[0][S2S ? t : 0][0]), pcr_me = smem_u32(&s_pcr[0][S2S ? t : 0][0]);
     const int v3 = lane & (NW - 1);                // this lane evaluates separator row v3 of level 3
     const unsigned pub_v = smem_u32(&s_pub[0][v3][0]), pub_vn = smem_u32(&s_pub[0][(v3 + 1) % NW][0]);
-    double c3P = s_l3[v3][0], c3Au = s_l3[v3][1], c3su = s_l3[v3][2], c3Nx = s_l3[v3][3];
-    double mW = s_minv[wid][v3], mM = (wid > 0) ? s_minv[(wid + NW - 1) % NW][v3] : 0.0;
-    const unsigned lane_me = smem_u32(&s_lane[0][S2S ? t : 0][0]);
-    if constexpr (S2S) {
-      sts128(lane_me, c3P, c3Au); sts128(lane_me + T * 16, c3su, c3Nx); sts128(lane_me + 2 * T * 16, mW, mM);
-      sts128(lane_me + 3 * T * 16, GL, GR); sts128(lane_me + 4 * T * 16, binv, 0.0);
-    }
+    const double c3P = s_l3[v3][0], c3Au = s_l3[v3][1], c3su = s_l3[v3][2], c3Nx = s_l3[v3][3];
+    const double mW = s_minv[wid][v3], mM = (wid > 0) ? s_minv[(wid + NW - 1) % NW][v3] : 0.0;
+    const int g8 = lane & 7;
     auto prefetch = [&](int jj, const double *src) {   // slice n-jj -> staging buffer jj&1
       if (STAGE && 2 * jj > n && jj <= n) {
         const unsigned dst = qo_me + (jj & 1) * QO_BUF;
@@ -350,55 +365,59 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
       if (STAGE) cp_async_commit();
     };
     prefetch(1, hr - SL);
+
+    // ------------------------------------------------------------------ the contour march
     for (int j = 1; j <= n; j++) {
       hw += SL; hr -= SL;
       const bool pairing = (2 * j > n);
       prefetch(j + 1, hr - SL);   // the slice the NEXT step pairs with; written >= 1 step ago by this thread
-      // right-hand side b = A q and the level-1 (chunk) solve with zero separators
+      // right-hand side b = A q and the level-1 (chunk) solve with zero separators, UL order
       double z[CA];
-      double zlast = 0.0, z0 = 0.0;
+      double zlast = 0.0, z0 = 0.0, zfn = 0.0;
       if constexpr (CI > 0) {
         if constexpr (UNI) {
-          // b_k = A_off (q_{k-1} + q_{k+1} + 4 q_k); u = forward sweep of b/A_off; z_k = ca_k u_k - be_k z_{k+1}
+          // b_k = A_off (q_{k-1} + q_{k+1} + 4 q_k); first sweep on u = b/A_off from the right end
 #pragma unroll
-          for (int k = 0; k < CI; k++) {
+          for (int k = CI - 1; k >= 0; k--) {
             double qm = (k == 0) ? XL : q[k - 1], qp = q[k + 1];
             double tk = fma(4.0, q[k], qm + qp);
-            z[k] = (k == 0) ? tk : fma(-al[k], z[k - 1], tk);
+            z[k] = (k == CI - 1) ? tk : fma(-al[k], z[k + 1], tk);
           }
-          z[CI - 1] = ca[CI - 1] * z[CI - 1];
+          z[0] = ca[0] * z[0];
+          zfn = shfl_dn_d(z[0], 1);            // z_first of the right neighbour: overlaps the second sweep
 #pragma unroll
-          for (int k = CI - 2; k >= 0; k--) z[k] = fma(-be[k], z[k + 1], ca[k] * z[k]);
+          for (int k = 1; k < CI; k++) z[k] = fma(-be[k], z[k - 1], ca[k] * z[k]);
         } else {
 #pragma unroll
-          for (int k = 0; k < CI; k++) {
+          for (int k = CI - 1; k >= 0; k--) {
             double qm = (k == 0) ? XL : q[k - 1], qp = q[k + 1];
             double bk = fma(ca[k], qm, fma(cu[k], qp, cd[k] * q[k]));
-            z[k] = (k == 0) ? bk : fma(-al[k], z[k - 1], bk);
+            z[k] = (k == CI - 1) ? bk : fma(-al[k], z[k + 1], bk);
           }
+          zfn = shfl_dn_d(z[0], 1);
 #pragma unroll
-          for (int k = CI - 2; k >= 0; k--) z[k] = fma(-be[k], z[k + 1], z[k]);
+          for (int k = 1; k < CI; k++) z[k] = fma(-be[k], z[k - 1], z[k]);
         }
         zlast = z[CI - 1]; z0 = z[0];
       }
       const double qprev = (CI > 0) ? q[CI > 0 ? CI - 1 : 0] : XL;
       double r = UNI ? sAd * fma(4.0, q[C - 1], qprev) : fma(sAl, qprev, sAd * q[C - 1]);   // UNI: sAd holds A_off
+      const double rnx = fma(UNI ? sAd : sAu, qn, (CI > 0) ? -su * zfn : 0.0);             // next-chunk terms
       if constexpr (CI > 0) r = fma(-sl, zlast, r);
       const double rsep = r;                              // lane 31: without next-warp terms
-      {
-        r = fma(UNI ? sAd : sAu, qn, r);
-        if constexpr (CI > 0) { double zfn = shfl_dn_d(z0, 1); r = fma(-su, zfn, r); }
-      }
-      r = (lane == 31) ? 0.0 : r;
-      // level 2
+      r = (lane == 31) ? 0.0 : r + rnx;
+      // level 2: three cyclic-reduction stages, then the 4x4 class inverse
 #pragma unroll
-      for (int s = 0; s < 5; s++) {
+      for (int s = 0; s < NST; s++) {
         const int d = 1 << s;
         double rm = shfl_up_d(r, d), rp = shfl_dn_d(r, d);
-        if constexpr (S2S) { const double2 ag = lds128(pcr_me + s * T * 16); r = fma(ag.x, rm, fma(ag.y, rp, r)); }
-        else r = fma(pa_[s], rm, fma(pg_[s], rp, r));
+        r = fma(pa_[s], rm, fma(pg_[s], rp, r));
       }
-      const double Z = r * (S2S ? lds64(lane_me + 4 * T * 16) : binv);
+      double Z;
+      {
+        double r0 = shfl_d(r, g8), r1 = shfl_d(r, g8 + 8), r2 = shfl_d(r, g8 + 16), r3 = shfl_d(r, g8 + 24);
+        Z = fma(inv4[0], r0, inv4[1] * r1) + fma(inv4[2], r2, inv4[3] * r3);
+      }
       // level 3: publish, one barrier, then every group of NW lanes solves the warp-separator system
       // cooperatively (lane v3 forms R_v3, butterfly sum over the group) -> every lane holds W_wid, W_wid-1
       const unsigned pbuf = (j & 1) * PUB_BUF;
@@ -408,16 +427,14 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
           " @p0 st.shared.v2.f64 [%1], {%2, %3};\n @p0 st.shared.f64 [%1+16], %4;\n"
           " @p30 st.shared.f64 [%1+32], %4;\n @p31 st.shared.f64 [%1+40], %5;\n}"
           ::"r"(lane), "r"(pub_me + pbuf), "d"(q[0]), "d"(z0), "d"(Z), "d"(rsep) : "memory");
+      double Zm = shfl_up_d(Z, 1);                 // left neighbour's warp-local separator value
+      Zm = (lane == 0) ? 0.0 : Zm;
       if constexpr (NW > 1) __syncthreads(); else __syncwarp();
       double Ww, Wm;
       {
         const double2 own = lds128(pub_v + pbuf + 32);     // Z30_v, rsep_v
         const double2 nxt = lds128(pub_vn + pbuf);         // qf_{v+1}, zf_{v+1}
         const double z0n = lds64(pub_vn + pbuf + 16);      // Z0_{v+1}
-        if constexpr (S2S) {
-          const double2 c01 = lds128(lane_me), c23 = lds128(lane_me + T * 16), mm = lds128(lane_me + 2 * T * 16);
-          c3P = c01.x; c3Au = c01.y; c3su = c23.x; c3Nx = c23.y; mW = mm.x; mM = mm.y;
-        }
         double R = fma(-c3P, own.x, own.y);
         double R2 = fma(c3Au, nxt.x, -c3su * nxt.y);
         R2 = fma(-c3Nx, z0n, R2);
@@ -429,11 +446,8 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
           Wm += __shfl_xor_sync(0xffffffffu, Wm, d);
         }
       }
-      double GLs = GL, GRs = GR;
-      if constexpr (S2S) { const double2 g = lds128(lane_me + 3 * T * 16); GLs = g.x; GRs = g.y; }
-      const double X = (lane == 31) ? Ww : fma(-GLs, Wm, fma(-GRs, Ww, Z));
-      double XLn = shfl_up_d(X, 1);
-      XLn = (lane == 0) ? Wm : XLn;
+      const double X = (lane == 31) ? Ww : fma(-GL, Wm, fma(-GR, Ww, Z));
+      const double XLn = fma(-GLm, Wm, fma(-GRm, Ww, Zm));   // lane 0: GLm = -1, GRm = Zm = 0 -> W_{wid-1}
       // level-1 correction
       if constexpr (CI > 0) {
 #pragma unroll
@@ -455,31 +469,18 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
 #pragma unroll
             for (int k = 0; k < C; k += 2) {
               const double2 v = STAGE ? lds128(src + (k / 2) * T * 16) : *reinterpret_cast<const double2 *>(hr + k * T);
-              if constexpr (S2S) {
-                const double2 ph = lds128(phi_me + (k / 2) * T * 16);
-                sts128(phi_me + (k / 2) * T * 16, fma(wj * q[k], v.x, ph.x), fma(wj * q[k + 1], v.y, ph.y));
-              } else {
-                phi[k] = fma(wj * q[k], v.x, phi[k]);
-                phi[k + 1] = fma(wj * q[k + 1], v.y, phi[k + 1]);
-              }
+              phi[k] = fma(wj * q[k], v.x, phi[k]);
+              phi[k + 1] = fma(wj * q[k + 1], v.y, phi[k + 1]);
             }
           }
         } else {
 #pragma unroll
           for (int k = 0; k < C; k++) phi[k] = fma(wj * q[k], q[k], phi[k]);
-          if constexpr (S2S) {   // the one unpaired slice (j = n/2) seeds the shared accumulators
-#pragma unroll
-            for (int k = 0; k < C; k += 2) sts128(phi_me + (k / 2) * T * 16, phi[k], phi[k + 1]);
-          }
         }
       }
     }
 
     // ------------------------------------------------------------------ residual, phi, Q
-    if constexpr (S2S) {
-#pragma unroll
-      for (int k = 0; k < C; k += 2) { const double2 ph = lds128(phi_me + (k / 2) * T * 16); phi[k] = ph.x; phi[k + 1] = ph.y; }
-    }
     double qsum = 0.0;
 #pragma unroll
     for (int k = 0; k < C; k++) {
