@@ -127,7 +127,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = host_cores()
-    per_step = max(cores, 8) * 4
+    per_step = max(cores, 8) * 16
     for _ in range(args.warmup):
         oracle_throughput(max(cores, 8), cores)
     t = []
@@ -273,6 +273,12 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         algo_bytes = P * ni * NSTEPS * BYTES_PER_DOF_STEP
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one march launch (ncu --set full capture)
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            tr = json.load(open(tpath))["march_ie_kernel"]
+            if tr["problems"] == P and tr["N"] == N_NODES and tr["nsteps"] == NSTEPS:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
         achieved = algo_bytes / (march_ms_avg * 1e-3) / 1e9
         line = {"metric": "propagator_dof_steps_per_s", "value": value, "unit": "DOF-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -286,13 +292,13 @@ def main():
                         "call": "scftb_residual_batch (pinned host buffers), wall clock, max over ranks"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "march_ie_kernel<8,uniform>",
+                             "traffic": traffic, "kernel": "march_ie_kernel<8,128,uniform>",
                              "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": march_ms_avg,
                              "peak_source": peak_src,
                              "bytes_per_dof_step": BYTES_PER_DOF_STEP}}
         if not args.no_cpu_baseline and world == 1:
             cores = host_cores()
-            cnt = max(cores, 8) * 8
+            cnt = max(cores, 8) * 160   # ~10-20 s of CPU work
             v, dt = oracle_throughput(cnt, cores)
             line["cpu_baseline"] = {"value": v, "unit": "DOF-steps/s", "cores": cores, "kind": "port",
                                     "sample": f"first {cnt} problems of the sweep, oracle/scft_oracle.c, {dt:.1f} s"}
