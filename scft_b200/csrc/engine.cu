@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "march1d.cuh"
+#include "march_irk4.cuh"
 
 namespace scftb {
 
@@ -147,6 +148,30 @@ int choose_kernel(int ni, bool uni, KernelChoice &kc) {
   return 0;
 }
 
+// IRK4 (complex solve): fewer nodes per thread, twice the coefficient storage
+int choose_kernel_irk4(int ni, KernelChoice &kc) {
+  int C = 1;
+  while (C < 8 && (ni + C - 1) / C > 256) C *= 2;
+  int need = (ni + C - 1) / C;
+  if (need > 256) return 1;
+  int T = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 256));
+  kc.fn = nullptr;
+  if (C == 1 && T == 32) kc.fn = (march_fn)march_irk4_kernel<1, 32>;
+  if (C == 1 && T == 64) kc.fn = (march_fn)march_irk4_kernel<1, 64>;
+  if (C == 1 && T == 128) kc.fn = (march_fn)march_irk4_kernel<1, 128>;
+  if (C == 1 && T == 256) kc.fn = (march_fn)march_irk4_kernel<1, 256>;
+  if (C == 2 && T == 256) kc.fn = (march_fn)march_irk4_kernel<2, 256>;
+  if (C == 4 && T == 256) kc.fn = (march_fn)march_irk4_kernel<4, 256>;
+  if (C == 8 && T == 256) kc.fn = (march_fn)march_irk4_kernel<8, 256>;
+  if (!kc.fn) return 1;
+  kc.C = C; kc.T = T;
+  return 0;
+}
+
+static int choose_any(int scheme, int ni, bool uni, KernelChoice &kc) {
+  return scheme == SCFTB_IRK4_CONSISTENT ? choose_kernel_irk4(ni, kc) : choose_kernel(ni, uni, kc);
+}
+
 }  // namespace scftb
 
 using namespace scftb;
@@ -183,8 +208,8 @@ long scftb_launch_count(int reset) {
 int scftb_create(const scftb_config *cfg, scftb_engine **out) {
   if (!cfg || !out) return fail(SCFTB_ERR_ARG, "null argument");
   if (cfg->N < 4 || cfg->nsteps < 2 || cfg->max_batch < 1) return fail(SCFTB_ERR_ARG, "N>=4, nsteps>=2, max_batch>=1");
-  if (cfg->scheme != SCFTB_IE_ROWSCALE && cfg->scheme != SCFTB_IE_CONSISTENT)
-    return fail(SCFTB_ERR_ARG, "scheme not supported by this build");
+  if (cfg->scheme != SCFTB_IE_ROWSCALE && cfg->scheme != SCFTB_IE_CONSISTENT && cfg->scheme != SCFTB_IRK4_CONSISTENT)
+    return fail(SCFTB_ERR_ARG, "unknown scheme");
   scftb_engine *e = new scftb_engine();
   e->cfg = *cfg;
   e->ni = cfg->N - 2;
@@ -205,7 +230,7 @@ int scftb_create(const scftb_config *cfg, scftb_engine **out) {
   // sum_j w_j q_j q_{n-j} = sum_{j>n/2} 2 w_j q_j q_{n-j} + [n even] w_{n/2} q_{n/2}^2
   std::vector<double> wq(e->h_w);
   for (int j = 0; j <= n; j++) wq[j] = (2 * j > n) ? 2.0 * e->h_w[j] : ((2 * j == n) ? e->h_w[j] : 0.0);
-  if (choose_kernel(e->ni, true, e->kc)) {
+  if (choose_any(cfg->scheme, e->ni, true, e->kc)) {
     delete e;
     return fail(SCFTB_ERR_ARG, "N too large for the register-resident march (N <= 4098 in this build)");
   }
@@ -289,7 +314,7 @@ int scftb_set_problem(scftb_engine *e, int p, double tau, double L, const double
     for (int q = 0; q < B; q++)
       for (int i = 0; i < N; i++) e->h_x[(size_t)q * N + i] = e->h_L[q] * i / (N - 1);
     e->uniform = false;
-    if (choose_kernel(e->ni, false, e->kc)) return fail(SCFTB_ERR_ARG, "N too large");
+    if (choose_any(e->cfg.scheme, e->ni, false, e->kc)) return fail(SCFTB_ERR_ARG, "N too large");
   }
   std::vector<double> xs(N);
   for (int q = (p < 0 ? 0 : p); q < (p < 0 ? B : p + 1); q++) {

@@ -99,12 +99,12 @@ __device__ __forceinline__ double eta_node(const MarchParams &P, int p, int i, d
   return a * em[P.ni - 2] + b * em[P.ni - 1];
 }
 
-struct Row { double Al, Ad, Au, Tl, Td, Tu; };
+struct Row { double Al, Ad, Au, Tl, Td, Tu, Dl, Dd, Du; };   // A (mass), T = A + dt*D, D = B + C
 
 // Row g (0-based interior index) of A (mass) and T = A + ds*(B + C).
 __device__ __forceinline__ Row assemble_row(const MarchParams &P, int p, int g, double L, double dt) {
   Row r;
-  if (g >= P.ni) { r.Al = r.Ad = r.Au = 0.0; r.Tl = r.Tu = 0.0; r.Td = 1.0; return r; }  // padding
+  if (g >= P.ni) { r.Al = r.Ad = r.Au = 0.0; r.Tl = r.Tu = 0.0; r.Td = 1.0; r.Dl = r.Du = 0.0; r.Dd = 0.0; return r; }  // padding
   const int i = g + 1;
   double a1, a2, bl, bd, bu;
   if (P.uniform) {  // 1D_FEM.c:61,95-98
@@ -127,11 +127,12 @@ __device__ __forceinline__ Row assemble_row(const MarchParams &P, int p, int g, 
     cu = a2 * (e0 + ep) / 12;
     cd = a1 * (em + 3 * e0) / 12 + a2 * (3 * e0 + ep) / 12;
   }
-  r.Tl = r.Al + dt * (bl + cl);
-  r.Td = r.Ad + dt * (bd + cd);
-  r.Tu = r.Au + dt * (bu + cu);
-  if (g == 0) { r.Al = 0.0; r.Tl = 0.0; }            // q(0,s) = 0   (1D_FEM.c:179-180,213)
-  if (g == P.ni - 1) { r.Au = 0.0; r.Tu = 0.0; }     // q(L,s) = 0   (1D_FEM.c:181-182,214)
+  r.Dl = bl + cl; r.Dd = bd + cd; r.Du = bu + cu;
+  r.Tl = r.Al + dt * r.Dl;
+  r.Td = r.Ad + dt * r.Dd;
+  r.Tu = r.Au + dt * r.Du;
+  if (g == 0) { r.Al = 0.0; r.Tl = 0.0; r.Dl = 0.0; }            // q(0,s) = 0   (1D_FEM.c:179-180,213)
+  if (g == P.ni - 1) { r.Au = 0.0; r.Tu = 0.0; r.Du = 0.0; }     // q(L,s) = 0   (1D_FEM.c:181-182,214)
   return r;
 }
 
