@@ -1,9 +1,9 @@
-mkdir -p gpurun_out
-python bench.py > gpurun_out/bench_r1_v4.json 2> gpurun_out/bench_r1_v4.err
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_r1_v4_reference.json 2>> gpurun_out/bench_r1_v4.err
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1_v4.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:march_ie -s 3 -c 1 -f -o gpurun_out/prof_march_r1_v4 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:anderson -s 3 -c 1 -f -o gpurun_out/prof_anderson_r1_v4 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full2.log 2>&1
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.limit --format=csv > gpurun_out/gpu_info.txt
-nproc >> gpurun_out/gpu_info.txt; lscpu | grep "Model name" >> gpurun_out/gpu_info.txt
-ls -la gpurun_out | tail -8
+python -m pytest tests/test_gpu_driver.py -m gpu -q --tb=short 2>&1 | grep -E "^E  |passed|failed|Error" | cut -c1-250 | head -20
+python - <<'PY'
+import numpy as np, scft_b200 as sb
+fx=np.load('tests/golden/ref_fixtures.npz')
+sb.write_solution('/tmp/N33.txt', float(fx['n33_error']), float(fx['n33_F']), fx['n33_x'], fx['n33_eta'])
+PY
+mkdir -p gpurun_out/conv
+./scft_b200/lib/drivescft_b200 /tmp/N33.txt --flow dealii --scheme irk4 --solver broydn --levels 6 --tol 1e-9 --outdir gpurun_out/conv | grep -E "^flow|^level" 
+./scft_b200/lib/drivescft_b200 /tmp/N33.txt --flow dealii --scheme ie_rowscale --solver broydn --levels 6 --tol 1e-9 --outdir /tmp | grep -E "^flow|^level" 

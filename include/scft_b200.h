@@ -139,6 +139,19 @@ int scftb_mixer_iterate_device(scftb_mixer *m, void *stream);
 int scftb_mixer_status(scftb_mixer *m, void *stream, int *done, int *iters, double *err);
 int scftb_mixer_get_x(scftb_mixer *m, void *stream, double *x /* host [nprob][N-2] */);
 
+/* ---- around the hot path: spline, refinement, result files ------------------- */
+/* spline_chen (spline_chen.c:12-106): mode 0 natural (m = 0), 1 not-a-knot (m == NULL), 2 y'' = bc at both
+ * ends; evaluates (and extrapolates) at xp.  Solved as a tridiagonal system, not dense gaussj. */
+int scftb_spline(const double *x, const double *y, const double *xp, double *yp, int Nx, int Nxp, int mode, double bc);
+/* refine_mesh (scft.cc:132-169): every cell cut in x, N -> 2N-1 nodes; the interior field is carried over by a
+ * not-a-knot spline through the old interior nodes.  x_new[2N-1], eta_mid_new[2N-3]. */
+int scftb_refine_mesh(int N, const double *x, const double *eta_mid, double *x_new, double *eta_mid_new);
+/* solution_yita_1D_N=<N>.txt writer (scft.cc:319-337) and reader (read_yita_middle_1D, scft_util.cc:13-41) */
+int scftb_write_solution(const char *path, int N, double err, double F, const double *x, const double *eta_full);
+int scftb_read_solution(const char *path, int *N, double *x, double *eta, int capacity);
+/* Exp_m*_n2048_IE.res reader (1D_FEM.c:322-342): rows of x/l, phi, eta after 9 header lines */
+int scftb_read_res(const char *path, int rows, double *xl, double *phi, double *eta);
+
 /* ---- measurement hooks ---------------------------------------------------------------------- */
 /* When on, every march-kernel launch is bracketed by CUDA events on its launching stream;
  * scftb_get_march_ms returns the summed device time and the number of launches since the last call. */

@@ -6,4 +6,5 @@ thin Python host mirror used by tests/ and bench.py; it fails loudly if the libr
 there is no CPU fallback.
 """
 from .engine import (Engine, lib, IE_ROWSCALE, IE_CONSISTENT, IRK4_CONSISTENT, QUAD_ROMBERG,  # noqa: F401
-                     QUAD_TRAPEZOID, TAU_REF, L_REF, ScftError, launch_count, LIB_PATH, AndersonBatch)
+                     QUAD_TRAPEZOID, TAU_REF, L_REF, ScftError, launch_count, LIB_PATH, AndersonBatch,
+                     spline, refine_mesh, write_solution, read_solution, read_res)

@@ -39,7 +39,8 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_bind_global", "scftb_callback_nr1", "scftb_callback_c0", "scftb_callback_fixedpoint_c0",
            "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_adm_chen_batch",
            "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
-           "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms"]
+           "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_write_solution",
+           "scftb_read_solution", "scftb_read_res"]
 
 
 def lib():
@@ -80,6 +81,11 @@ def lib():
         L.scftb_mixer_get_x.argtypes = [C.c_void_p, C.c_void_p, _dp]
         L.scftb_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.scftb_get_march_ms.argtypes = [C.c_void_p, _dp, _ip]
+        L.scftb_spline.argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double]
+        L.scftb_refine_mesh.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
+        L.scftb_write_solution.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_double, _dp, _dp]
+        L.scftb_read_solution.argtypes = [C.c_char_p, _ip, _dp, _dp, C.c_int]
+        L.scftb_read_res.argtypes = [C.c_char_p, C.c_int, _dp, _dp, _dp]
         _lib = L
     return _lib
 
@@ -227,3 +233,39 @@ class AndersonBatch:
         out = np.zeros((self.nprob, self.eng.ni))
         _chk(lib().scftb_mixer_get_x(self._h, C.c_void_p(stream_ptr), _p(out)))
         return out
+
+
+def spline(x, y, xp, mode=0, bc=0.0):
+    """scftb_spline: mode 0 natural, 1 not-a-knot, 2 given second derivative"""
+    x, y, xp = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, xp))
+    yp = np.zeros_like(xp)
+    _chk(lib().scftb_spline(_p(x), _p(y), _p(xp), _p(yp), len(x), len(xp), mode, bc))
+    return yp
+
+
+def refine_mesh(x, eta_mid):
+    """scftb_refine_mesh: (x_new[2N-1], eta_mid_new[2N-3])"""
+    x, eta_mid = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(eta_mid, dtype=np.float64)
+    N = len(x)
+    xn, en = np.zeros(2 * N - 1), np.zeros(2 * N - 3)
+    _chk(lib().scftb_refine_mesh(N, _p(x), _p(eta_mid), _p(xn), _p(en)))
+    return xn, en
+
+
+def write_solution(path, err, F, x, eta_full):
+    x, eta_full = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(eta_full, dtype=np.float64)
+    _chk(lib().scftb_write_solution(path.encode(), len(x), err, F, _p(x), _p(eta_full)))
+
+
+def read_solution(path):
+    n = C.c_int(0)
+    _chk(lib().scftb_read_solution(path.encode(), C.byref(n), None, None, 0))
+    x, eta = np.zeros(n.value), np.zeros(n.value)
+    _chk(lib().scftb_read_solution(path.encode(), C.byref(n), _p(x), _p(eta), n.value))
+    return x, eta
+
+
+def read_res(path, rows):
+    xl, phi, eta = np.zeros(rows), np.zeros(rows), np.zeros(rows)
+    _chk(lib().scftb_read_res(path.encode(), rows, _p(xl), _p(phi), _p(eta)))
+    return xl, phi, eta

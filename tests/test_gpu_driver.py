@@ -1,0 +1,73 @@
+"""The C++ host driver (scft_b200/host/drivescft_b200.cpp) with the control flow of the reference's
+mains: drivescft.cc:259-322 (read -> [broydn -> save -> refine] x levels) and 1D_FEM.c:289-370."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "scft_b200", "lib", "drivescft_b200")
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import scft_b200
+    scft_b200.lib()
+    if not os.path.exists(DRIVER):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "scft_b200", "csrc"), "all"], check=True)
+    return scft_b200
+
+
+def run_driver(args):
+    p = subprocess.run([DRIVER] + args, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    rows = []
+    for ln in p.stdout.splitlines():
+        m = re.match(r"level (\d+): N=(\d+) check=(\d+) Error= (\S+) mean_field_free_energy=(\S+) Q=(\S+)", ln)
+        if m:
+            rows.append(dict(level=int(m[1]), N=int(m[2]), check=int(m[3]), err=float(m[4]), F=float(m[5]), Q=float(m[6])))
+    return rows
+
+
+def test_dealii_flow_two_refinement_levels(sb, oracle, fixtures, tmp_path):
+    inp = str(tmp_path / "N=33_for_read.txt")
+    sb.write_solution(inp, float(fixtures["n33_error"]), float(fixtures["n33_F"]), fixtures["n33_x"], fixtures["n33_eta"])
+    rows = run_driver([inp, "--flow", "dealii", "--scheme", "irk4", "--solver", "broydn", "--levels", "3", "--tol", "1e-10",
+                       "--outdir", str(tmp_path)])
+    assert [r["N"] for r in rows] == [33, 65, 129]
+    # level 0: the reference's own converged file; its recorded free energy
+    assert rows[0]["err"] < 3e-9 and rows[0]["F"] == pytest.approx(float(fixtures["n33_F"]), abs=1e-11)
+    for r in rows:
+        assert r["err"] < 1e-8
+    # free energy moves monotonically towards the fine-mesh value (Exp_m1024 header f = 1.9097e-3)
+    assert rows[0]["F"] > rows[1]["F"] > rows[2]["F"] > float(fixtures["res1024_f"])
+    # the saved files are in the reference format and re-evaluate to the reported residual on the ORACLE
+    for r in rows:
+        x, eta = sb.read_solution(str(tmp_path / f"solution_yita_1D_N={r['N']:03d}.txt"))
+        assert len(x) == r["N"]
+        ref = oracle.residual(oracle.eta_full(x, eta[1:-1]), oracle.f0_given(x), scheme=oracle.IRK4_CONSISTENT, nsteps=2048)
+        assert np.abs(ref["out"]).max() < 1.5e-8
+        assert oracle.free_energy(x, oracle.eta_full(x, eta[1:-1])) == pytest.approx(r["F"], abs=1e-11)
+
+
+def test_dealii_flow_staged_anderson(sb, fixtures, tmp_path):
+    inp = str(tmp_path / "N=33_for_read.txt")
+    eta = fixtures["n33_eta"].copy()
+    eta[1:-1] *= 1.02
+    sb.write_solution(inp, 0.0, 0.0, fixtures["n33_x"], eta)
+    rows = run_driver([inp, "--flow", "dealii", "--scheme", "ie", "--solver", "adm_chen", "--levels", "1", "--tol", "1e-8",
+                       "--nsteps", "256", "--outdir", str(tmp_path)])
+    assert rows[0]["N"] == 33 and rows[0]["err"] < 1e-7
+
+
+def test_1dfem_flow(sb, fixtures, tmp_path):
+    res = str(tmp_path / "Exp_m32_n2048_IE.res")
+    with open(res, "w") as fh:
+        fh.write("\n\nm = 32   n = 2048\n\nN=1000\nZ=1\n\n x/l phi eta phie phij\n-----\n")
+        for a, b, c in zip(fixtures["res32_xl"], fixtures["res32_phi"], fixtures["res32_eta"]):
+            fh.write(f" {a:.6e}  {b:.14e}  {c:.14e}  0.0  0.0\n")
+    rows = run_driver([res, "--flow", "1dfem", "--outdir", str(tmp_path)])
+    assert rows[0]["N"] == 33 and rows[0]["err"] < 1e-7     # broydn err = 1e-8 (1D_FEM.c:350)
