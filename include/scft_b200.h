@@ -152,6 +152,38 @@ int scftb_read_solution(const char *path, int *N, double *x, double *eta, int ca
 /* Exp_m*_n2048_IE.res reader (1D_FEM.c:322-342): rows of x/l, phi, eta after 9 header lines */
 int scftb_read_res(const char *path, int rows, double *xl, double *phi, double *eta);
 
+/* ---- the 2-D path: Q1 mesh, CSR matrices, Jacobi-PCG per contour step (BASELINE.json configs[3],[4]) ------
+ * Structured nx x ny cells on [0,L] x [0,Ly], DOF d = ix*(ny+1)+iy, Dirichlet q = 0 on x = 0 and x = L
+ * (scft.cc:599-606), matrices A, B, C of scft.cc:643-656, implicit-Euler step (A + ds(B+C)) q+ = A q solved by
+ * conjugate gradients (the role of solve_time_step, scft.cc:698-705).  world > 1: slab partition in x over
+ * `world` ranks (one process per GPU), halo exchange and dot products over NCCL. */
+typedef struct scftb2d_engine scftb2d_engine;
+typedef struct {
+  int nx, ny;          /* cells in x and y */
+  double L, Ly, tau;   /* domain and surface-layer width (phi0 depends on x only) */
+  int nsteps;          /* contour steps */
+  int quadrature;      /* SCFTB_QUAD_* */
+  double sign;         /* +1: phi0 - phi */
+  double rtol;         /* CG stops at ||r|| <= rtol ||b|| (<= 0: 1e-12) */
+  int maxit;           /* CG iteration limit per step (<= 0: 100000) */
+  int device;          /* CUDA device ordinal of this rank */
+  int rank, world;     /* slab partition */
+  int store_history;   /* keep all slices instead of the half the quadrature re-reads */
+} scftb2d_config;
+/* rank 0 obtains the NCCL id and hands the 128 bytes to every rank (e.g. through torch.distributed) */
+int scftb2d_nccl_unique_id(char *id128);
+int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128 /* NULL when world == 1 */, scftb2d_engine **out);
+int scftb2d_destroy(scftb2d_engine *e);
+/* global row range [row0, row0+nrows) owned by this rank */
+int scftb2d_rows(scftb2d_engine *e, int *row0, int *nrows);
+/* eta on ALL (nx+1)(ny+1) nodes (host) -> sign*(phi0 - phi) on this rank's rows (host, nrows values) */
+int scftb2d_residual(scftb2d_engine *e, const double *eta, double *out);
+int scftb2d_get_phi(scftb2d_engine *e, double *phi /* nrows */);
+int scftb2d_get_stats(scftb2d_engine *e, long long *cg_iterations, double *march_ms);
+/* CSR view (global column indices) of this rank's rows of T = A + ds(B+C) and A after the last assembly:
+ * rowptr[nrows+1], colind/valT/valA[<= 9*nrows] */
+int scftb2d_export_csr(scftb2d_engine *e, int *rowptr, int *colind, double *valT, double *valA);
+
 /* ---- measurement hooks ---------------------------------------------------------------------- */
 /* When on, every march-kernel launch is bracketed by CUDA events on its launching stream;
  * scftb_get_march_ms returns the summed device time and the number of launches since the last call. */

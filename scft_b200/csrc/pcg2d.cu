@@ -1,0 +1,635 @@
+// pcg2d.cu — the 2-D path: Q1 finite elements on a structured nx x ny mesh of [0,L] x [0,Ly],
+// implicit-Euler contour march with a Jacobi-preconditioned conjugate-gradient solve per step
+// (BASELINE.json configs[3], [4]).
+//
+// Reference: the deal.II matrices A, B, C of scft.cc:643-656 (2x2 Gauss on Q1 cells, Dirichlet on
+// x = 0, L via scft.cc:599-606), sparsity from setup_system (scft.cc:546-549), and the CG-per-step
+// pattern of the dead solve_time_step (scft.cc:698-705) / step-26.cc:224-241.  The live reference
+// stepper (IRK4 block system) is non-symmetric, so the CG-able form is the implicit-Euler step
+// (A + ds (B + C)) q+ = A q, which is SPD.
+//
+// Design
+//   * assembly: one thread per row writes the 9-point rows of T = A + ds(B+C) and A straight into a
+//     sliced-ELL layout (slices of 32 rows, 9 slots, slot-major inside a slice) so that a warp's
+//     loads of values and column indices are contiguous; the CSR view is exported for inspection.
+//   * solve: Chronopoulos-Gear CG (one fused reduction per iteration) with a Jacobi preconditioner.
+//     Single GPU: the WHOLE contour march — right-hand sides, all CG iterations of all steps,
+//     history stores and the fused density quadrature — is ONE persistent cooperative kernel with
+//     grid-wide barriers; reductions are per-block partials summed in a fixed order by every block
+//     (deterministic, no atomics).
+//   * multi GPU: slab partition in x (contiguous row blocks, one node column of halo per side);
+//     the same device code runs as two short kernels per CG iteration with an NCCL halo exchange
+//     (grouped ncclSend/ncclRecv to the <= 2 neighbours) and ONE ncclAllReduce of 3 doubles between
+//     them.  Convergence is decided on the device from the all-reduced scalars, identically on
+//     every rank; the host polls the flag every few iterations.
+#include <cooperative_groups.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace cg = cooperative_groups;
+using namespace scftb;
+
+namespace scftb {
+
+constexpr int SLOTS = 9;
+constexpr int TPB2 = 256;
+
+struct Sys2D {
+  int nx, ny, nyp;          // cells, nodes per column
+  int row0, nrows;          // first owned global row, owned rows (whole node columns)
+  int halo;                 // halo entries on each side (nyp or 0)
+  int nslices;              // ceil(nrows/32)
+  double hx, hy, dt;
+  const double *eta;        // [ndof_global] field on all nodes
+  int *col;                 // SELL: [nslices][9][32], LOCAL vector index (halo_left + owned + halo_right)
+  double *valT, *valA;      // same layout
+  double *dinv;             // [nrows] 1 / diag(T)
+};
+
+struct Vec2D {
+  double *q, *x, *r, *z, *s, *p, *w, *b;   // z carries halos: z[-halo .. nrows+halo); others [nrows]
+};
+
+struct Red2D {
+  double *partial;          // [2][grid][4] per-block partial sums
+  double *scal;             // [8]: gamma, delta, rr, bb | gamma_old, alpha_old, converged, iterations-in-step
+};
+
+__device__ __forceinline__ size_t sell(int row, int k) { return (size_t)(row >> 5) * (SLOTS * 32) + k * 32 + (row & 31); }
+
+// ------------------------------------------------------------------------------------------------
+// assembly of row `i` (local) = global row row0 + i
+__global__ void assemble2d_kernel(Sys2D S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.nslices * 32) return;
+  double vT[SLOTS], vA[SLOTS];
+  int cl[SLOTS];
+#pragma unroll
+  for (int k = 0; k < SLOTS; k++) { vT[k] = 0.0; vA[k] = 0.0; cl[k] = S.halo + min(i, S.nrows - 1); }
+  if (i < S.nrows) {
+    const int g = S.row0 + i, ix = g / S.nyp, iy = g - ix * S.nyp;
+    const bool wall = (ix == 0 || ix == S.nx);
+    if (wall) {
+      vT[4] = 1.0;   // identity row: q = 0 on x = 0, L (scft.cc:599-606)
+    } else {
+      const double hx = S.hx, hy = S.hy, jxw = hx * hy / 4;
+      const double gm = (1.0 - 0.5773502691896257) / 2, gp = (1.0 + 0.5773502691896257) / 2;
+      for (int ex = ix - 1; ex <= ix; ex++) {
+        if (ex < 0 || ex >= S.nx) continue;
+        for (int ey = iy - 1; ey <= iy; ey++) {
+          if (ey < 0 || ey >= S.ny) continue;
+          const int ax = ix - ex, ay = iy - ey;
+          double en[2][2];   // eta at the element's nodes [bx][by]
+#pragma unroll
+          for (int bx = 0; bx < 2; bx++)
+#pragma unroll
+            for (int by = 0; by < 2; by++) en[bx][by] = S.eta[(size_t)(ex + bx) * S.nyp + ey + by];
+#pragma unroll
+          for (int bx = 0; bx < 2; bx++)
+#pragma unroll
+            for (int by = 0; by < 2; by++) {
+              const int slot = (bx - ax + 1) * 3 + (by - ay + 1);
+              const double mx = (ax == bx) ? 2.0 : 1.0, my = (ay == by) ? 2.0 : 1.0;
+              const double kx = (ax == bx) ? 1.0 : -1.0, ky = (ay == by) ? 1.0 : -1.0;
+              const double a = (hx / 6) * (hy / 6) * mx * my;                               // (phi_a, phi_b)
+              const double b = (kx / hx) * (hy / 6) * my + (hx / 6) * mx * (ky / hy);         // (grad phi_a, grad phi_b)
+              double c = 0.0;                                                                // (eta_h phi_a, phi_b), 2x2 Gauss
+#pragma unroll
+              for (int qx = 0; qx < 2; qx++)
+#pragma unroll
+                for (int qy = 0; qy < 2; qy++) {
+                  const double u1 = qx ? gp : gm, u0 = 1 - u1, v1 = qy ? gp : gm, v0 = 1 - v1;   // shape values at the point
+                  const double sa = (ax ? u1 : u0) * (ay ? v1 : v0), sb = (bx ? u1 : u0) * (by ? v1 : v0);
+                  const double eh = en[0][0] * u0 * v0 + en[1][0] * u1 * v0 + en[0][1] * u0 * v1 + en[1][1] * u1 * v1;
+                  c += sa * sb * eh * jxw;
+                }
+              vA[slot] += a;
+              vT[slot] += a + S.dt * (b + c);
+            }
+        }
+      }
+    }
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++)
+#pragma unroll
+      for (int dy = -1; dy <= 1; dy++) {
+        const int slot = (dx + 1) * 3 + (dy + 1), jx = ix + dx, jy = iy + dy;
+        if (jx < 0 || jx > S.nx || jy < 0 || jy >= S.nyp || jx == 0 || jx == S.nx) {
+          if (!(dx == 0 && dy == 0)) { vT[slot] = 0.0; vA[slot] = 0.0; }   // outside, or a Dirichlet column
+          if (dx == 0 && dy == 0) vA[slot] = wall ? 0.0 : vA[slot];
+        } else {
+          cl[slot] = S.halo + (jx * S.nyp + jy - S.row0);
+        }
+      }
+    S.dinv[i] = 1.0 / vT[4];
+  }
+#pragma unroll
+  for (int k = 0; k < SLOTS; k++) { S.col[sell(i, k)] = cl[k]; S.valT[sell(i, k)] = vT[k]; S.valA[sell(i, k)] = vA[k]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// building blocks shared by the persistent kernel and the multi-GPU step kernels
+struct Part { double a, b, c, d; };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// block-level sum of 4 values -> partial[block][0..3]
+__device__ void block_partials(Part v, double *out) {
+  __shared__ double sh[4][TPB2 / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v.a = warp_sum(v.a); v.b = warp_sum(v.b); v.c = warp_sum(v.c); v.d = warp_sum(v.d);
+  if (lane == 0) { sh[0][w] = v.a; sh[1][w] = v.b; sh[2][w] = v.c; sh[3][w] = v.d; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+    for (int i = 0; i < TPB2 / 32; i++) s += sh[threadIdx.x][i];
+    out[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// fixed-order sum over the blocks' partials (every block computes the same value)
+__device__ Part reduce_partials(const double *partial, int nblocks) {
+  Part t = {0, 0, 0, 0};
+  __shared__ double tot[4];
+  if (threadIdx.x < 32) {
+    double a = 0, b = 0, c = 0, d = 0;
+    for (int i = threadIdx.x; i < nblocks; i += 32) {
+      a += partial[4 * i]; b += partial[4 * i + 1]; c += partial[4 * i + 2]; d += partial[4 * i + 3];
+    }
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+    if (threadIdx.x == 0) { tot[0] = a; tot[1] = b; tot[2] = c; tot[3] = d; }
+  }
+  __syncthreads();
+  t.a = tot[0]; t.b = tot[1]; t.c = tot[2]; t.d = tot[3];
+  __syncthreads();
+  return t;
+}
+
+// start of a contour step: b = A q, initial guess x = q, r = b - T x, z = D^-1 r, p = w = 0; partial bb = b.b
+__device__ Part step_begin(const Sys2D &S, const Vec2D &V, int tid, int nthreads) {
+  Part acc = {0, 0, 0, 0};
+  for (int i = tid; i < S.nslices * 32; i += nthreads) {
+    if (i >= S.nrows) continue;
+    double bq = 0.0, tq = 0.0;
+#pragma unroll
+    for (int k = 0; k < SLOTS; k++) {
+      const double qv = V.q[S.col[sell(i, k)] - S.halo + 0];   // q is stored like z (with halos), see host
+      bq = fma(S.valA[sell(i, k)], qv, bq);
+      tq = fma(S.valT[sell(i, k)], qv, tq);
+    }
+    const double r = bq - tq;
+    V.b[i] = bq; V.x[i] = V.q[i]; V.r[i] = r; V.z[i] = S.dinv[i] * r; V.p[i] = 0.0; V.w[i] = 0.0;
+    acc.d = fma(bq, bq, acc.d);
+  }
+  return acc;
+}
+
+// s = T z; partial sums gamma = r.z, delta = z.s, rr = r.r
+__device__ Part cg_spmv(const Sys2D &S, const Vec2D &V, int tid, int nthreads) {
+  Part acc = {0, 0, 0, 0};
+  for (int i = tid; i < S.nslices * 32; i += nthreads) {
+    if (i >= S.nrows) continue;
+    double sv = 0.0;
+#pragma unroll
+    for (int k = 0; k < SLOTS; k++) sv = fma(S.valT[sell(i, k)], V.z[S.col[sell(i, k)] - S.halo], sv);
+    V.s[i] = sv;
+    const double r = V.r[i], z = V.z[i];
+    acc.a = fma(r, z, acc.a); acc.b = fma(z, sv, acc.b); acc.c = fma(r, r, acc.c);
+  }
+  return acc;
+}
+
+// p = z + beta p; w = s + beta w; x += alpha p; r -= alpha w; z = D^-1 r
+__device__ void cg_update(const Sys2D &S, const Vec2D &V, double alpha, double beta, int tid, int nthreads) {
+  for (int i = tid; i < S.nrows; i += nthreads) {
+    const double p = fma(beta, V.p[i], V.z[i]), w = fma(beta, V.w[i], V.s[i]);
+    V.p[i] = p; V.w[i] = w;
+    V.x[i] = fma(alpha, p, V.x[i]);
+    const double r = fma(-alpha, w, V.r[i]);
+    V.r[i] = r; V.z[i] = S.dinv[i] * r;
+  }
+}
+
+struct March2D {
+  Sys2D S; Vec2D V; Red2D R;
+  int nsteps, maxit, store_full;
+  double rtol;
+  const double *wq;       // pair weights
+  double *hist;           // [nslices_hist][nrows]
+  double *phi;            // [nrows]
+  long long *iters;       // total CG iterations
+};
+
+// end of a contour step: q = x, history store, fused quadrature
+__device__ void step_end(const March2D &M, int j, int tid, int nthreads) {
+  const int n = M.nsteps;
+  const bool pairing = 2 * j > n;
+  const double wj = (2 * j >= n) ? M.wq[j] : 0.0;
+  for (int i = tid; i < M.S.nrows; i += nthreads) {
+    const double qv = M.V.x[i];
+    M.V.q[i] = qv;
+    if (M.store_full || 2 * j < n) M.hist[(size_t)j * M.S.nrows + i] = qv;
+    if (2 * j >= n) {
+      const double qo = pairing ? M.hist[(size_t)(n - j) * M.S.nrows + i] : qv;
+      M.phi[i] = fma(wj * qv, qo, M.phi[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// single GPU: the whole march in one persistent cooperative kernel
+__global__ void __launch_bounds__(TPB2) march2d_persistent_kernel(March2D M) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const Sys2D &S = M.S; const Vec2D &V = M.V;
+  int slot = 0;
+  long long iters = 0;
+  for (int i = tid; i < S.nrows; i += nthreads) {   // q(x,0) = 1 inside, 0 on the walls (drivescft.cc:120-127)
+    const int ix = (S.row0 + i) / S.nyp;
+    const double q0 = (ix == 0 || ix == S.nx) ? 0.0 : 1.0;
+    V.q[i] = q0; M.phi[i] = 0.0; M.hist[i] = q0;
+  }
+  grid.sync();
+  for (int j = 1; j <= M.nsteps; j++) {
+    Part pb = step_begin(S, V, tid, nthreads);
+    block_partials(pb, M.R.partial + ((size_t)slot * gridDim.x + blockIdx.x) * 4);
+    grid.sync();
+    const double bb = reduce_partials(M.R.partial + (size_t)slot * gridDim.x * 4, gridDim.x).d;
+    slot ^= 1;
+    const double tol2 = M.rtol * M.rtol * bb;
+    double gamma_old = 1.0, alpha_old = 1.0;
+    for (int it = 0; it < M.maxit; it++) {
+      Part pa = cg_spmv(S, V, tid, nthreads);
+      block_partials(pa, M.R.partial + ((size_t)slot * gridDim.x + blockIdx.x) * 4);
+      grid.sync();
+      const Part t = reduce_partials(M.R.partial + (size_t)slot * gridDim.x * 4, gridDim.x);
+      slot ^= 1;
+      if (t.c <= tol2) break;                                  // ||r|| <= rtol ||b||
+      const double beta = (it == 0) ? 0.0 : t.a / gamma_old;
+      const double alpha = (it == 0) ? t.a / t.b : t.a / (t.b - beta * t.a / alpha_old);
+      cg_update(S, V, alpha, beta, tid, nthreads);
+      gamma_old = t.a; alpha_old = alpha;
+      iters++;
+      grid.sync();
+    }
+    step_end(M, j, tid, nthreads);
+    grid.sync();
+  }
+  if (tid == 0) *M.iters = iters;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi GPU: the same pieces as short kernels; scalars live in R.scal (all-reduced by NCCL in between)
+__global__ void init2d_kernel(March2D M) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  for (int i = tid; i < M.S.nrows; i += nthreads) {
+    const int ix = (M.S.row0 + i) / M.S.nyp;
+    const double q0 = (ix == 0 || ix == M.S.nx) ? 0.0 : 1.0;
+    M.V.q[i] = q0; M.phi[i] = 0.0; M.hist[i] = q0;
+  }
+  if (tid == 0) *M.iters = 0;
+}
+__global__ void __launch_bounds__(TPB2) step_begin_kernel(March2D M) {   // needs q halos; leaves bb partials
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  Part pb = step_begin(M.S, M.V, tid, nthreads);
+  block_partials(pb, M.R.partial + (size_t)blockIdx.x * 4);
+}
+__global__ void __launch_bounds__(TPB2) spmv_kernel(March2D M) {         // needs z halos; leaves gamma, delta, rr partials
+  if (M.R.scal[6] != 0.0) return;                                         // converged: nothing to do
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  Part pa = cg_spmv(M.S, M.V, tid, nthreads);
+  block_partials(pa, M.R.partial + (size_t)blockIdx.x * 4);
+}
+// one block: partials -> scal[0..3] (local sums; NCCL all-reduces them in place afterwards)
+__global__ void fold_partials_kernel(March2D M, int nblocks, int first) {
+  if (!first && M.R.scal[6] != 0.0) { if (threadIdx.x < 4) M.R.scal[threadIdx.x] = 0.0; return; }
+  Part t = reduce_partials(M.R.partial, nblocks);
+  if (threadIdx.x == 0) { M.R.scal[0] = t.a; M.R.scal[1] = t.b; M.R.scal[2] = t.c; M.R.scal[3] = t.d; }
+}
+__global__ void __launch_bounds__(TPB2) begin_finish_kernel(March2D M) {  // after the all-reduce of bb
+  if (blockIdx.x == 0 && threadIdx.x == 0) { M.R.scal[7] = M.R.scal[3]; M.R.scal[6] = 0.0; M.R.scal[4] = 1.0; M.R.scal[5] = 1.0; M.R.scal[8] = 0.0; }
+}
+__global__ void __launch_bounds__(TPB2) update_kernel(March2D M) {        // after the all-reduce of gamma, delta, rr
+  __shared__ double sa, sb;
+  __shared__ int done;
+  if (threadIdx.x == 0) {
+    const double gam = M.R.scal[0], del = M.R.scal[1], rr = M.R.scal[2], bb = M.R.scal[7];
+    const int first = (M.R.scal[8] == 0.0);
+    done = (M.R.scal[6] != 0.0) || (rr <= M.rtol * M.rtol * bb);
+    const double beta = first ? 0.0 : gam / M.R.scal[4];
+    sa = first ? gam / del : gam / (del - beta * gam / M.R.scal[5]);
+    sb = beta;
+  }
+  __syncthreads();
+  const bool fin = done;
+  const double alpha = sa, beta = sb;
+  cg::grid_group grid = cg::this_grid();
+  if (!fin) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    cg_update(M.S, M.V, alpha, beta, tid, nthreads);
+  }
+  grid.sync();   // every block has read the old scalars before block 0 overwrites them
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (fin) M.R.scal[6] = 1.0;
+    else { M.R.scal[4] = M.R.scal[0]; M.R.scal[5] = alpha; M.R.scal[8] += 1.0; *M.iters += 1; }
+  }
+}
+__global__ void __launch_bounds__(TPB2) step_end_kernel(March2D M, int j) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  step_end(M, j, tid, nthreads);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library has no link-time dependency on it (single-GPU use needs none)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct Nccl {
+  void *h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId *);
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  int (*CommDestroy)(ncclComm_t);
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*GroupStart)();
+  int (*GroupEnd)();
+  const char *(*GetErrorString)(int);
+  bool load() {
+    if (h) return true;
+    for (const char *nm : {"libnccl.so.2", "libnccl.so"}) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) return false;
+#define SYM(f, n) f = (decltype(f))dlsym(h, n); if (!f) return false
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllReduce, "ncclAllReduce"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return true;
+  }
+};
+static Nccl g_nccl;
+constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;   // ncclFloat64, ncclSum (nccl.h)
+
+}  // namespace scftb
+
+struct scftb2d_engine {
+  scftb2d_config cfg;
+  int nyp, ndof, ix0, ix1, nrows, halo, nslices, grid_persist, grid_step;
+  cudaStream_t stream;
+  ncclComm_t comm;
+  March2D M;
+  double *d_eta, *d_qbuf, *d_zbuf, *d_out, *d_f0;
+  std::vector<double> h_f0x, h_w;
+  long long last_iters;
+  double last_ms;
+};
+
+#define NK(call)                                                                                              \
+  do {                                                                                                        \
+    int _r = (call);                                                                                          \
+    if (_r != 0) return fail(SCFTB_ERR_CUDA, std::string(#call) + ": " + g_nccl.GetErrorString(_r));           \
+  } while (0)
+
+extern "C" {
+
+int scftb2d_nccl_unique_id(char *id128) {
+  if (!g_nccl.load()) return fail(SCFTB_ERR_STATE, "libnccl.so.2 not found");
+  ncclUniqueId id;
+  NK(g_nccl.GetUniqueId(&id));
+  memcpy(id128, id.internal, 128);
+  return SCFTB_OK;
+}
+
+int scftb2d_destroy(scftb2d_engine *e) {
+  if (!e) return SCFTB_OK;
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->stream);
+  if (e->comm) g_nccl.CommDestroy(e->comm);
+  for (void *p : {(void *)e->M.S.col, (void *)e->M.S.valT, (void *)e->M.S.valA, (void *)e->M.S.dinv, (void *)e->d_eta,
+                  (void *)e->d_qbuf, (void *)e->d_zbuf, (void *)e->M.V.x, (void *)e->M.V.r, (void *)e->M.V.s, (void *)e->M.V.p,
+                  (void *)e->M.V.w, (void *)e->M.V.b, (void *)e->M.R.partial, (void *)e->M.R.scal, (void *)e->M.hist,
+                  (void *)e->M.phi, (void *)e->M.iters, (void *)e->d_out, (void *)e->d_f0, (void *)e->M.wq})
+    if (p) cudaFree(p);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return SCFTB_OK;
+}
+
+int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_engine **out) {
+  if (!cfg || !out) return fail(SCFTB_ERR_ARG, "null argument");
+  if (cfg->nx < 2 || cfg->ny < 1 || cfg->nsteps < 2 || cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world)
+    return fail(SCFTB_ERR_ARG, "bad 2-D configuration");
+  if (cfg->world > 1 && (cfg->nx + 1) / cfg->world < 2) return fail(SCFTB_ERR_ARG, "too few node columns per rank");
+  scftb2d_engine *e = new scftb2d_engine();
+  memset(&e->M, 0, sizeof(e->M));
+  e->cfg = *cfg; e->comm = nullptr; e->d_eta = e->d_qbuf = e->d_zbuf = e->d_out = e->d_f0 = nullptr; e->last_iters = 0; e->last_ms = 0;
+  const int nx = cfg->nx, ny = cfg->ny, nyp = ny + 1, n = cfg->nsteps;
+  e->nyp = nyp; e->ndof = (nx + 1) * nyp;
+  // slab partition: node columns [ix0, ix1) (1-D slab along x, one node column of halo per neighbour)
+  e->ix0 = (int)((long long)(nx + 1) * cfg->rank / cfg->world);
+  e->ix1 = (int)((long long)(nx + 1) * (cfg->rank + 1) / cfg->world);
+  e->nrows = (e->ix1 - e->ix0) * nyp;
+  e->halo = cfg->world > 1 ? nyp : 0;
+  e->nslices = (e->nrows + 31) / 32;
+  if (cfg->quadrature == SCFTB_QUAD_ROMBERG) {
+    if (romberg_weights(n, 1.0 / n, e->h_w)) { delete e; return fail(SCFTB_ERR_ARG, "Romberg needs nsteps = 2^k >= 16"); }
+  } else trapezoid_weights(n, 1.0 / n, e->h_w);
+  std::vector<double> wq(n + 1);
+  for (int j = 0; j <= n; j++) wq[j] = (2 * j > n) ? 2.0 * e->h_w[j] : ((2 * j == n) ? e->h_w[j] : 0.0);
+  std::vector<double> xs(nx + 1);
+  for (int i = 0; i <= nx; i++) xs[i] = cfg->L * i / nx;
+  e->h_f0x.resize(nx + 1);
+  f0_given(nx + 1, xs.data(), cfg->tau, e->h_f0x.data());
+#define CK2(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { int rc = fail(SCFTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); scftb2d_destroy(e); return rc; } } while (0)
+  CK2(cudaSetDevice(cfg->device));
+  CK2(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  const size_t nr = e->nrows, nv = (size_t)e->nslices * SLOTS * 32, nh = nr + 2 * (size_t)e->halo;
+  Sys2D &S = e->M.S;
+  S.nx = nx; S.ny = ny; S.nyp = nyp; S.row0 = e->ix0 * nyp; S.nrows = e->nrows; S.halo = e->halo; S.nslices = e->nslices;
+  S.hx = cfg->L / nx; S.hy = cfg->Ly / ny; S.dt = 1.0 / n;
+  CK2(cudaMalloc(&S.col, sizeof(int) * nv));
+  CK2(cudaMalloc(&S.valT, sizeof(double) * nv));
+  CK2(cudaMalloc(&S.valA, sizeof(double) * nv));
+  CK2(cudaMalloc(&S.dinv, sizeof(double) * nr));
+  CK2(cudaMalloc(&e->d_eta, sizeof(double) * e->ndof));
+  S.eta = e->d_eta;
+  CK2(cudaMalloc(&e->d_qbuf, sizeof(double) * nh));
+  CK2(cudaMalloc(&e->d_zbuf, sizeof(double) * nh));
+  CK2(cudaMemset(e->d_qbuf, 0, sizeof(double) * nh));
+  CK2(cudaMemset(e->d_zbuf, 0, sizeof(double) * nh));
+  Vec2D &V = e->M.V;
+  V.q = e->d_qbuf + e->halo; V.z = e->d_zbuf + e->halo;
+  for (double **p : {&V.x, &V.r, &V.s, &V.p, &V.w, &V.b}) CK2(cudaMalloc(p, sizeof(double) * nr));
+  e->M.nsteps = n; e->M.maxit = cfg->maxit > 0 ? cfg->maxit : 100000; e->M.rtol = cfg->rtol > 0 ? cfg->rtol : 1e-12;
+  e->M.store_full = cfg->store_history;
+  const size_t nsl = cfg->store_history ? n + 1 : n / 2 + 1;
+  CK2(cudaMalloc(&e->M.hist, sizeof(double) * nsl * nr));
+  CK2(cudaMalloc(&e->M.phi, sizeof(double) * nr));
+  CK2(cudaMalloc(&e->M.iters, sizeof(long long)));
+  CK2(cudaMalloc(&e->d_out, sizeof(double) * nr));
+  CK2(cudaMalloc(&e->d_f0, sizeof(double) * (nx + 1)));
+  CK2(cudaMemcpy(e->d_f0, e->h_f0x.data(), sizeof(double) * (nx + 1), cudaMemcpyHostToDevice));
+  double *dwq = nullptr;
+  CK2(cudaMalloc(&dwq, sizeof(double) * (n + 1)));
+  CK2(cudaMemcpy(dwq, wq.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice));
+  e->M.wq = dwq;
+  int sms = 0, occ = 0;
+  CK2(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march2d_persistent_kernel, TPB2, 0));
+  occ = std::max(1, std::min(occ, 4));
+  e->grid_persist = sms * occ;
+  int occ2 = 0;
+  CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, update_kernel, TPB2, 0));
+  e->grid_step = sms * std::max(1, std::min(occ2, 4));
+  const int gmax = std::max(e->grid_persist, e->grid_step);
+  CK2(cudaMalloc(&e->M.R.partial, sizeof(double) * 2 * gmax * 4));
+  CK2(cudaMalloc(&e->M.R.scal, sizeof(double) * 16));
+  CK2(cudaMemset(e->M.R.scal, 0, sizeof(double) * 16));
+  if (cfg->world > 1) {
+    if (!nccl_id128) { scftb2d_destroy(e); return fail(SCFTB_ERR_ARG, "world > 1 needs the NCCL unique id of rank 0"); }
+    if (!g_nccl.load()) { scftb2d_destroy(e); return fail(SCFTB_ERR_STATE, "libnccl.so.2 not found"); }
+    ncclUniqueId id;
+    memcpy(id.internal, nccl_id128, 128);
+    int r = g_nccl.CommInitRank(&e->comm, cfg->world, id, cfg->rank);
+    if (r != 0) { int rc = fail(SCFTB_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); scftb2d_destroy(e); return rc; }
+  }
+  *out = e;
+  return SCFTB_OK;
+}
+
+// exchange the one-column halos of v (device pointer to the owned part; halos live just outside it)
+static int halo_exchange(scftb2d_engine *e, double *v) {
+  const int r = e->cfg.rank, w = e->cfg.world, h = e->halo, nr = e->nrows;
+  NK(g_nccl.GroupStart());
+  if (r > 0) { NK(g_nccl.Send(v, h, NCCL_DOUBLE, r - 1, e->comm, e->stream)); NK(g_nccl.Recv(v - h, h, NCCL_DOUBLE, r - 1, e->comm, e->stream)); }
+  if (r + 1 < w) { NK(g_nccl.Send(v + nr - h, h, NCCL_DOUBLE, r + 1, e->comm, e->stream)); NK(g_nccl.Recv(v + nr, h, NCCL_DOUBLE, r + 1, e->comm, e->stream)); }
+  NK(g_nccl.GroupEnd());
+  return SCFTB_OK;
+}
+
+// eta: field on ALL (nx+1)(ny+1) nodes (host), out: sign*(phi0 - phi) on this rank's rows (host, nrows values)
+int scftb2d_residual(scftb2d_engine *e, const double *eta, double *out) {
+  if (!e || !eta || !out) return fail(SCFTB_ERR_ARG, "null argument");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = e->stream;
+  CK(cudaMemcpyAsync(e->d_eta, eta, sizeof(double) * e->ndof, cudaMemcpyHostToDevice, st));
+  assemble2d_kernel<<<(e->nslices * 32 + 255) / 256, 256, 0, st>>>(e->M.S);
+  g_launches++;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, st));
+  March2D M = e->M;
+  if (e->cfg.world == 1) {
+    void *args[] = {&M};
+    CK(cudaLaunchCooperativeKernel((void *)march2d_persistent_kernel, dim3(e->grid_persist), dim3(TPB2), args, 0, st));
+    g_launches++;
+  } else {
+    const int G = e->grid_step;
+    init2d_kernel<<<G, TPB2, 0, st>>>(M);
+    g_launches++;
+    double flag[1];
+    for (int j = 1; j <= M.nsteps; j++) {
+      int rc = halo_exchange(e, M.V.q);
+      if (rc) return rc;
+      step_begin_kernel<<<G, TPB2, 0, st>>>(M);
+      fold_partials_kernel<<<1, 32, 0, st>>>(M, G, 1);
+      NK(g_nccl.AllReduce(M.R.scal, M.R.scal, 4, NCCL_DOUBLE, NCCL_SUM, e->comm, st));
+      begin_finish_kernel<<<1, 32, 0, st>>>(M);
+      g_launches += 3;
+      bool conv = false;
+      for (int it = 0; it < M.maxit && !conv; it++) {
+        rc = halo_exchange(e, M.V.z);
+        if (rc) return rc;
+        spmv_kernel<<<G, TPB2, 0, st>>>(M);
+        fold_partials_kernel<<<1, 32, 0, st>>>(M, G, 0);
+        NK(g_nccl.AllReduce(M.R.scal, M.R.scal, 3, NCCL_DOUBLE, NCCL_SUM, e->comm, st));
+        void *args[] = {&M};
+        CK(cudaLaunchCooperativeKernel((void *)update_kernel, dim3(G), dim3(TPB2), args, 0, st));
+        g_launches += 3;
+        if (it % 8 == 7) {   // poll the device-side convergence flag (identical on every rank)
+          CK(cudaMemcpyAsync(flag, M.R.scal + 6, sizeof(double), cudaMemcpyDeviceToHost, st));
+          CK(cudaStreamSynchronize(st));
+          conv = flag[0] != 0.0;
+        }
+      }
+      step_end_kernel<<<G, TPB2, 0, st>>>(M, j);
+      g_launches++;
+    }
+  }
+  CK(cudaEventRecord(e1, st));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  e->last_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CK(cudaMemcpy(&e->last_iters, M.iters, sizeof(long long), cudaMemcpyDeviceToHost));
+  std::vector<double> phi(e->nrows);
+  CK(cudaMemcpy(phi.data(), M.phi, sizeof(double) * e->nrows, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < e->nrows; i++) {
+    const int ix = e->ix0 + i / e->nyp;
+    out[i] = (ix == 0 || ix == e->cfg.nx) ? 0.0 : e->cfg.sign * (e->h_f0x[ix] - phi[i]);
+  }
+  return SCFTB_OK;
+}
+
+int scftb2d_rows(scftb2d_engine *e, int *row0, int *nrows) {
+  if (!e) return fail(SCFTB_ERR_ARG, "null engine");
+  if (row0) *row0 = e->ix0 * e->nyp;
+  if (nrows) *nrows = e->nrows;
+  return SCFTB_OK;
+}
+
+int scftb2d_get_phi(scftb2d_engine *e, double *phi) {
+  if (!e || !phi) return fail(SCFTB_ERR_ARG, "null argument");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaMemcpy(phi, e->M.phi, sizeof(double) * e->nrows, cudaMemcpyDeviceToHost));
+  return SCFTB_OK;
+}
+
+int scftb2d_get_stats(scftb2d_engine *e, long long *cg_iterations, double *march_ms) {
+  if (!e) return fail(SCFTB_ERR_ARG, "null engine");
+  if (cg_iterations) *cg_iterations = e->last_iters;
+  if (march_ms) *march_ms = e->last_ms;
+  return SCFTB_OK;
+}
+
+// CSR view of this rank's rows of T and A (global column indices), for inspection and tests.
+// rowptr[nrows+1], colind/valT/valA[9*nrows] (entries with value 0 in both matrices are dropped)
+int scftb2d_export_csr(scftb2d_engine *e, int *rowptr, int *colind, double *valT, double *valA) {
+  if (!e || !rowptr || !colind || !valT || !valA) return fail(SCFTB_ERR_ARG, "null argument");
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t nv = (size_t)e->nslices * SLOTS * 32;
+  std::vector<int> col(nv);
+  std::vector<double> vt(nv), va(nv);
+  CK(cudaMemcpy(col.data(), e->M.S.col, sizeof(int) * nv, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(vt.data(), e->M.S.valT, sizeof(double) * nv, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(va.data(), e->M.S.valA, sizeof(double) * nv, cudaMemcpyDeviceToHost));
+  int nnz = 0;
+  for (int i = 0; i < e->nrows; i++) {
+    rowptr[i] = nnz;
+    for (int k = 0; k < SLOTS; k++) {
+      size_t s = (size_t)(i >> 5) * (SLOTS * 32) + k * 32 + (i & 31);
+      if (vt[s] == 0.0 && va[s] == 0.0) continue;
+      colind[nnz] = col[s] - e->halo + e->ix0 * e->nyp;
+      valT[nnz] = vt[s]; valA[nnz] = va[s];
+      nnz++;
+    }
+  }
+  rowptr[e->nrows] = nnz;
+  return SCFTB_OK;
+}
+
+}  // extern "C"

@@ -30,6 +30,13 @@ class _Config(C.Structure):
                 ("sign", C.c_double), ("max_batch", C.c_int), ("device", C.c_int), ("store_history", C.c_int)]
 
 
+class _Config2D(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("L", C.c_double), ("Ly", C.c_double), ("tau", C.c_double),
+                ("nsteps", C.c_int), ("quadrature", C.c_int), ("sign", C.c_double), ("rtol", C.c_double),
+                ("maxit", C.c_int), ("device", C.c_int), ("rank", C.c_int), ("world", C.c_int),
+                ("store_history", C.c_int)]
+
+
 _lib = None
 
 # every symbol include/scft_b200.h declares
@@ -40,7 +47,8 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_adm_chen_batch",
            "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
            "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_write_solution",
-           "scftb_read_solution", "scftb_read_res"]
+           "scftb_read_solution", "scftb_read_res", "scftb2d_nccl_unique_id", "scftb2d_create", "scftb2d_destroy",
+           "scftb2d_rows", "scftb2d_residual", "scftb2d_get_phi", "scftb2d_get_stats", "scftb2d_export_csr"]
 
 
 def lib():
@@ -86,6 +94,14 @@ def lib():
         L.scftb_write_solution.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_double, _dp, _dp]
         L.scftb_read_solution.argtypes = [C.c_char_p, _ip, _dp, _dp, C.c_int]
         L.scftb_read_res.argtypes = [C.c_char_p, C.c_int, _dp, _dp, _dp]
+        L.scftb2d_nccl_unique_id.argtypes = [C.c_char_p]
+        L.scftb2d_create.argtypes = [C.POINTER(_Config2D), C.c_char_p, C.POINTER(C.c_void_p)]
+        L.scftb2d_destroy.argtypes = [C.c_void_p]
+        L.scftb2d_rows.argtypes = [C.c_void_p, _ip, _ip]
+        L.scftb2d_residual.argtypes = [C.c_void_p, _dp, _dp]
+        L.scftb2d_get_phi.argtypes = [C.c_void_p, _dp]
+        L.scftb2d_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), _dp]
+        L.scftb2d_export_csr.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp]
         _lib = L
     return _lib
 
@@ -269,3 +285,58 @@ def read_res(path, rows):
     xl, phi, eta = np.zeros(rows), np.zeros(rows), np.zeros(rows)
     _chk(lib().scftb_read_res(path.encode(), rows, _p(xl), _p(phi), _p(eta)))
     return xl, phi, eta
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _chk(lib().scftb2d_nccl_unique_id(buf))
+    return buf.raw
+
+
+class Engine2D:
+    """2-D Q1 mesh, CSR matrices, Jacobi-PCG per contour step (scftb2d_*).  world > 1: slab partition
+    in x; pass the 128-byte NCCL id obtained on rank 0 (nccl_unique_id()) to every rank."""
+
+    def __init__(self, nx, ny, L=L_REF, Ly=None, tau=TAU_REF, nsteps=64, quadrature=QUAD_ROMBERG, sign=1.0,
+                 rtol=1e-12, maxit=0, device=0, rank=0, world=1, nccl_id=None, store_history=False):
+        Ly = L / nx * ny if Ly is None else Ly
+        self.nx, self.ny, self.ndof = nx, ny, (nx + 1) * (ny + 1)
+        cfg = _Config2D(nx, ny, L, Ly, tau, nsteps, quadrature, sign, rtol, maxit, device, rank, world, int(store_history))
+        h = C.c_void_p()
+        _chk(lib().scftb2d_create(C.byref(cfg), nccl_id, C.byref(h)))
+        self._h = h
+        r0, nr = C.c_int(0), C.c_int(0)
+        _chk(lib().scftb2d_rows(h, C.byref(r0), C.byref(nr)))
+        self.row0, self.nrows = r0.value, nr.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().scftb2d_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def residual(self, eta):
+        eta = np.ascontiguousarray(eta, dtype=np.float64)
+        assert eta.size == self.ndof
+        out = np.zeros(self.nrows)
+        _chk(lib().scftb2d_residual(self._h, _p(eta), _p(out)))
+        return out
+
+    def phi(self):
+        a = np.zeros(self.nrows)
+        _chk(lib().scftb2d_get_phi(self._h, _p(a)))
+        return a
+
+    def stats(self):
+        it, ms = C.c_longlong(0), C.c_double(0)
+        _chk(lib().scftb2d_get_stats(self._h, C.byref(it), C.byref(ms)))
+        return it.value, ms.value
+
+    def csr(self):
+        rowptr = np.zeros(self.nrows + 1, dtype=np.int32)
+        colind = np.zeros(9 * self.nrows, dtype=np.int32)
+        vt, va = np.zeros(9 * self.nrows), np.zeros(9 * self.nrows)
+        _chk(lib().scftb2d_export_csr(self._h, rowptr.ctypes.data_as(_ip), colind.ctypes.data_as(_ip), _p(vt), _p(va)))
+        nnz = rowptr[-1]
+        return rowptr, colind[:nnz], vt[:nnz], va[:nnz]

@@ -54,8 +54,8 @@ def test_library_exports_every_declared_symbol(L):
     import re, os
     import scft_b200
     hdr = open(os.path.join(os.path.dirname(scft_b200.__file__), "..", "include", "scft_b200.h")).read()
-    declared = set(re.findall(r"\b(scftb_[A-Za-z0-9_]+)\s*\(", hdr)) | {"scftb_funcerr"}
-    declared -= {"scftb_func"}
+    declared = set(re.findall(r"\b(scftb(?:2d)?_[A-Za-z0-9_]+)\s*\(", hdr)) | {"scftb_funcerr"}
+    declared -= {"scftb_func", "scftb2d_engine", "scftb2d_config"}
     assert declared == set(scft_b200.engine.EXPORTS)
     for s in sorted(declared):
         assert hasattr(L, s), s
