@@ -1,9 +1,3 @@
-python -m pytest tests/test_gpu_driver.py -m gpu -q --tb=short 2>&1 | grep -E "^E  |passed|failed|Error" | cut -c1-250 | head -20
-python - <<'PY'
-import numpy as np, scft_b200 as sb
-fx=np.load('tests/golden/ref_fixtures.npz')
-sb.write_solution('/tmp/N33.txt', float(fx['n33_error']), float(fx['n33_F']), fx['n33_x'], fx['n33_eta'])
-PY
-mkdir -p gpurun_out/conv
-./scft_b200/lib/drivescft_b200 /tmp/N33.txt --flow dealii --scheme irk4 --solver broydn --levels 6 --tol 1e-9 --outdir gpurun_out/conv | grep -E "^flow|^level" 
-./scft_b200/lib/drivescft_b200 /tmp/N33.txt --flow dealii --scheme ie_rowscale --solver broydn --levels 6 --tol 1e-9 --outdir /tmp | grep -E "^flow|^level" 
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_pcg2d.py 2>&1 | grep -E "rank|MGPU|Error|error" | tail -8
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tools/bench2d_multi.py 1023 1023 256 2>&1 | grep -E "world|Error|error" | tail -3
+python tools/bench2d.py 1023 1023 256 2>&1 | tail -1

@@ -60,7 +60,8 @@ struct Vec2D {
 
 struct Red2D {
   double *partial;          // [2][grid][4] per-block partial sums
-  double *scal;             // [8]: gamma, delta, rr, bb | gamma_old, alpha_old, converged, iterations-in-step
+  double *scal;             // [0..3] reduced gamma, delta, rr, bb; then two state records of 8 doubles at [8], [16]:
+                            //   0 gamma_old, 1 alpha_old, 2 converged, 3 bb, 4 CG iterations done in this step
 };
 
 __device__ __forceinline__ size_t sell(int row, int k) { return (size_t)(row >> 5) * (SLOTS * 32) + k * 32 + (row & 31); }
@@ -307,44 +308,41 @@ __global__ void __launch_bounds__(TPB2) step_begin_kernel(March2D M) {   // need
   Part pb = step_begin(M.S, M.V, tid, nthreads);
   block_partials(pb, M.R.partial + (size_t)blockIdx.x * 4);
 }
-__global__ void __launch_bounds__(TPB2) spmv_kernel(March2D M) {         // needs z halos; leaves gamma, delta, rr partials
-  if (M.R.scal[6] != 0.0) return;                                         // converged: nothing to do
+__global__ void __launch_bounds__(TPB2) spmv_kernel(March2D M, int par) {   // needs z halos; leaves gamma, delta, rr partials
+  if (M.R.scal[8 + 8 * par + 2] != 0.0) return;                              // converged: nothing to do
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   Part pa = cg_spmv(M.S, M.V, tid, nthreads);
   block_partials(pa, M.R.partial + (size_t)blockIdx.x * 4);
 }
 // one block: partials -> scal[0..3] (local sums; NCCL all-reduces them in place afterwards)
-__global__ void fold_partials_kernel(March2D M, int nblocks, int first) {
-  if (!first && M.R.scal[6] != 0.0) { if (threadIdx.x < 4) M.R.scal[threadIdx.x] = 0.0; return; }
+__global__ void fold_partials_kernel(March2D M, int nblocks, int par) {
+  if (par >= 0 && M.R.scal[8 + 8 * par + 2] != 0.0) { if (threadIdx.x < 4) M.R.scal[threadIdx.x] = 0.0; return; }
   Part t = reduce_partials(M.R.partial, nblocks);
   if (threadIdx.x == 0) { M.R.scal[0] = t.a; M.R.scal[1] = t.b; M.R.scal[2] = t.c; M.R.scal[3] = t.d; }
 }
-__global__ void __launch_bounds__(TPB2) begin_finish_kernel(March2D M) {  // after the all-reduce of bb
-  if (blockIdx.x == 0 && threadIdx.x == 0) { M.R.scal[7] = M.R.scal[3]; M.R.scal[6] = 0.0; M.R.scal[4] = 1.0; M.R.scal[5] = 1.0; M.R.scal[8] = 0.0; }
-}
-__global__ void __launch_bounds__(TPB2) update_kernel(March2D M) {        // after the all-reduce of gamma, delta, rr
-  __shared__ double sa, sb;
-  __shared__ int done;
-  if (threadIdx.x == 0) {
-    const double gam = M.R.scal[0], del = M.R.scal[1], rr = M.R.scal[2], bb = M.R.scal[7];
-    const int first = (M.R.scal[8] == 0.0);
-    done = (M.R.scal[6] != 0.0) || (rr <= M.rtol * M.rtol * bb);
-    const double beta = first ? 0.0 : gam / M.R.scal[4];
-    sa = first ? gam / del : gam / (del - beta * gam / M.R.scal[5]);
-    sb = beta;
+__global__ void begin_finish_kernel(March2D M) {   // after the all-reduce of bb: reset state record 0
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double *st = M.R.scal + 8;
+    st[0] = 1.0; st[1] = 1.0; st[2] = 0.0; st[3] = M.R.scal[3]; st[4] = 0.0;
   }
-  __syncthreads();
-  const bool fin = done;
-  const double alpha = sa, beta = sb;
-  cg::grid_group grid = cg::this_grid();
+}
+// after the all-reduce of gamma, delta, rr: reads state record `par`, writes record `par^1` (no grid barrier needed)
+__global__ void __launch_bounds__(TPB2) update_kernel(March2D M, int par) {
+  const double *st = M.R.scal + 8 + 8 * par;
+  double *sn = M.R.scal + 8 + 8 * (par ^ 1);
+  const double gam = M.R.scal[0], del = M.R.scal[1], rr = M.R.scal[2], bb = st[3];
+  const bool first = (st[4] == 0.0);
+  const bool fin = (st[2] != 0.0) || (rr <= M.rtol * M.rtol * bb);
+  const double beta = first ? 0.0 : gam / st[0];
+  const double alpha = first ? gam / del : gam / (del - beta * gam / st[1]);
   if (!fin) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     cg_update(M.S, M.V, alpha, beta, tid, nthreads);
   }
-  grid.sync();   // every block has read the old scalars before block 0 overwrites them
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (fin) M.R.scal[6] = 1.0;
-    else { M.R.scal[4] = M.R.scal[0]; M.R.scal[5] = alpha; M.R.scal[8] += 1.0; *M.iters += 1; }
+    sn[3] = bb;
+    if (fin) { sn[0] = st[0]; sn[1] = st[1]; sn[2] = 1.0; sn[4] = st[4]; }
+    else { sn[0] = gam; sn[1] = alpha; sn[2] = 0.0; sn[4] = st[4] + 1.0; *M.iters += 1; }
   }
 }
 __global__ void __launch_bounds__(TPB2) step_end_kernel(March2D M, int j) {
@@ -394,6 +392,8 @@ struct scftb2d_engine {
   std::vector<double> h_f0x, h_w;
   long long last_iters;
   double last_ms;
+  cudaGraphExec_t graph_exec;
+  double *h_flag;   // pinned
 };
 
 #define NK(call)                                                                                              \
@@ -416,6 +416,8 @@ int scftb2d_destroy(scftb2d_engine *e) {
   if (!e) return SCFTB_OK;
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  if (e->h_flag) cudaFreeHost(e->h_flag);
   if (e->comm) g_nccl.CommDestroy(e->comm);
   for (void *p : {(void *)e->M.S.col, (void *)e->M.S.valT, (void *)e->M.S.valA, (void *)e->M.S.dinv, (void *)e->d_eta,
                   (void *)e->d_qbuf, (void *)e->d_zbuf, (void *)e->M.V.x, (void *)e->M.V.r, (void *)e->M.V.s, (void *)e->M.V.p,
@@ -434,7 +436,7 @@ int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_en
   if (cfg->world > 1 && (cfg->nx + 1) / cfg->world < 2) return fail(SCFTB_ERR_ARG, "too few node columns per rank");
   scftb2d_engine *e = new scftb2d_engine();
   memset(&e->M, 0, sizeof(e->M));
-  e->cfg = *cfg; e->comm = nullptr; e->d_eta = e->d_qbuf = e->d_zbuf = e->d_out = e->d_f0 = nullptr; e->last_iters = 0; e->last_ms = 0;
+  e->cfg = *cfg; e->comm = nullptr; e->d_eta = e->d_qbuf = e->d_zbuf = e->d_out = e->d_f0 = nullptr; e->last_iters = 0; e->last_ms = 0; e->graph_exec = nullptr; e->h_flag = nullptr;
   const int nx = cfg->nx, ny = cfg->ny, nyp = ny + 1, n = cfg->nsteps;
   e->nyp = nyp; e->ndof = (nx + 1) * nyp;
   // slab partition: node columns [ix0, ix1) (1-D slab along x, one node column of halo per neighbour)
@@ -491,12 +493,13 @@ int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_en
   occ = std::max(1, std::min(occ, 4));
   e->grid_persist = sms * occ;
   int occ2 = 0;
-  CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, update_kernel, TPB2, 0));
+  CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, spmv_kernel, TPB2, 0));
   e->grid_step = sms * std::max(1, std::min(occ2, 4));
   const int gmax = std::max(e->grid_persist, e->grid_step);
   CK2(cudaMalloc(&e->M.R.partial, sizeof(double) * 2 * gmax * 4));
-  CK2(cudaMalloc(&e->M.R.scal, sizeof(double) * 16));
-  CK2(cudaMemset(e->M.R.scal, 0, sizeof(double) * 16));
+  CK2(cudaMalloc(&e->M.R.scal, sizeof(double) * 32));
+  CK2(cudaMemset(e->M.R.scal, 0, sizeof(double) * 32));
+  CK2(cudaMallocHost(&e->h_flag, sizeof(double) * 4));
   if (cfg->world > 1) {
     if (!nccl_id128) { scftb2d_destroy(e); return fail(SCFTB_ERR_ARG, "world > 1 needs the NCCL unique id of rank 0"); }
     if (!g_nccl.load()) { scftb2d_destroy(e); return fail(SCFTB_ERR_STATE, "libnccl.so.2 not found"); }
@@ -539,30 +542,41 @@ int scftb2d_residual(scftb2d_engine *e, const double *eta, double *out) {
     const int G = e->grid_step;
     init2d_kernel<<<G, TPB2, 0, st>>>(M);
     g_launches++;
-    double flag[1];
+    // 8 CG iterations (halo exchange, SpMV + partial dots, fold, all-reduce, update) captured once as a CUDA
+    // graph and replayed; the device-side convergence flag is polled after every replay
+    constexpr int ITERS_PER_GRAPH = 8;
+    if (!e->graph_exec) {
+      cudaGraph_t graph;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      for (int it = 0; it < ITERS_PER_GRAPH; it++) {
+        const int par = it & 1;
+        int rc = halo_exchange(e, M.V.z);
+        if (rc) { cudaStreamEndCapture(st, &graph); return rc; }
+        spmv_kernel<<<G, TPB2, 0, st>>>(M, par);
+        fold_partials_kernel<<<1, 32, 0, st>>>(M, G, par);
+        NK(g_nccl.AllReduce(M.R.scal, M.R.scal, 3, NCCL_DOUBLE, NCCL_SUM, e->comm, st));
+        update_kernel<<<G, TPB2, 0, st>>>(M, par);
+      }
+      CK(cudaStreamEndCapture(st, &graph));
+      CK(cudaGraphInstantiate(&e->graph_exec, graph, 0));
+      CK(cudaGraphDestroy(graph));
+    }
+    double *flag = e->h_flag;
     for (int j = 1; j <= M.nsteps; j++) {
       int rc = halo_exchange(e, M.V.q);
       if (rc) return rc;
       step_begin_kernel<<<G, TPB2, 0, st>>>(M);
-      fold_partials_kernel<<<1, 32, 0, st>>>(M, G, 1);
+      fold_partials_kernel<<<1, 32, 0, st>>>(M, G, -1);
       NK(g_nccl.AllReduce(M.R.scal, M.R.scal, 4, NCCL_DOUBLE, NCCL_SUM, e->comm, st));
       begin_finish_kernel<<<1, 32, 0, st>>>(M);
       g_launches += 3;
       bool conv = false;
-      for (int it = 0; it < M.maxit && !conv; it++) {
-        rc = halo_exchange(e, M.V.z);
-        if (rc) return rc;
-        spmv_kernel<<<G, TPB2, 0, st>>>(M);
-        fold_partials_kernel<<<1, 32, 0, st>>>(M, G, 0);
-        NK(g_nccl.AllReduce(M.R.scal, M.R.scal, 3, NCCL_DOUBLE, NCCL_SUM, e->comm, st));
-        void *args[] = {&M};
-        CK(cudaLaunchCooperativeKernel((void *)update_kernel, dim3(G), dim3(TPB2), args, 0, st));
-        g_launches += 3;
-        if (it % 8 == 7) {   // poll the device-side convergence flag (identical on every rank)
-          CK(cudaMemcpyAsync(flag, M.R.scal + 6, sizeof(double), cudaMemcpyDeviceToHost, st));
-          CK(cudaStreamSynchronize(st));
-          conv = flag[0] != 0.0;
-        }
+      for (int it = 0; it < M.maxit && !conv; it += ITERS_PER_GRAPH) {
+        CK(cudaGraphLaunch(e->graph_exec, st));
+        g_launches += 3 * ITERS_PER_GRAPH;
+        CK(cudaMemcpyAsync(flag, M.R.scal + 8 + 2, sizeof(double), cudaMemcpyDeviceToHost, st));   // record 0 (even count)
+        CK(cudaStreamSynchronize(st));
+        conv = flag[0] != 0.0;
       }
       step_end_kernel<<<G, TPB2, 0, st>>>(M, j);
       g_launches++;
