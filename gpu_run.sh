@@ -1,3 +1,2 @@
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_pcg2d.py 2>&1 | grep -E "rank|MGPU|Error|error" | tail -8
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tools/bench2d_multi.py 1023 1023 256 2>&1 | grep -E "world|Error|error" | tail -3
-python tools/bench2d.py 1023 1023 256 2>&1 | tail -1
+python -m pytest tests -m gpu -q 2>&1 | tail -4
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
