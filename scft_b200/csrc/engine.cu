@@ -296,6 +296,7 @@ int scftb_engine_max_batch(scftb_engine *e) { return e ? e->cfg.max_batch : 0; }
 
 int scftb_destroy(scftb_engine *e) {
   if (!e) return SCFTB_OK;
+  scftb_unbind_engine(e);
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   for (double *p : {e->d_eta, e->d_out, e->d_phi, e->d_Q, e->d_f0, e->d_L, e->d_x, e->d_eta_bnd, e->d_w, e->d_hist,

@@ -65,3 +65,4 @@ int upload_params(scftb_engine *e);
 
 // internal accessor (not part of the public ABI)
 extern "C" int scftb_engine_max_batch(scftb_engine *e);
+extern "C" void scftb_unbind_engine(scftb_engine *e);

@@ -71,6 +71,9 @@ int gauss_jordan(std::vector<double> &a, int n, std::vector<double> &b, bool nud
 extern "C" {
 
 // ------------------------------------------------------------------------------------------------
+// called by scftb_destroy: a destroyed engine must not stay bound
+void scftb_unbind_engine(scftb_engine *e) { if (g_bound == e) g_bound = nullptr; }
+
 int scftb_bind_global(scftb_engine *e) {
   g_bound = e;
   scftb_funcerr = 0;

@@ -1,0 +1,84 @@
+"""Error behaviour and edge cases of the C ABI on the GPU box: argument validation, size limits,
+NaN propagation (the reference exit(1)s, ADM_chen_C.c:61-66; the library returns a status)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+_dp = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import scft_b200
+    scft_b200.lib()
+    return scft_b200
+
+
+def test_argument_validation(sb):
+    with pytest.raises(sb.ScftError, match="Romberg"):
+        sb.Engine(33, nsteps=100)                      # romint needs n = 2^k >= 16 (romint.c:28-33)
+    with pytest.raises(sb.ScftError, match="N too large"):
+        sb.Engine(5000, nsteps=16)                     # register-resident march: N <= 4098
+    with pytest.raises(sb.ScftError):
+        sb.Engine(3, nsteps=16)
+    with pytest.raises(sb.ScftError, match="unknown scheme"):
+        sb.Engine(33, nsteps=16, scheme=7)
+    eng = sb.Engine(33, nsteps=16, max_batch=2)
+    with pytest.raises(sb.ScftError, match="nprob"):
+        eng.residual(np.zeros((3, 31)))                # more problems than the engine holds
+    with pytest.raises(sb.ScftError, match="store_history"):
+        eng.q_history()
+    eng.close()
+
+
+def test_smallest_and_largest_meshes(sb, oracle):
+    for N, n in [(4, 16), (5, 16), (34, 16), (4098, 16)]:
+        rng = np.random.default_rng(N)
+        x = oracle.mesh_uniform(N)
+        em = rng.standard_normal(N - 2)
+        eng = sb.Engine(N, nsteps=n, scheme=1)
+        eng.residual(em)
+        ref = oracle.residual(oracle.eta_full(x, em), oracle.f0_given(x), scheme=1, nsteps=n)
+        assert np.abs(eng.phi() - ref["phi"]).max() < 1e-10 * np.abs(ref["phi"]).max()
+        eng.close()
+
+
+def test_nan_field_is_reported_not_fatal(sb, fixtures):
+    eng = sb.Engine(33, nsteps=16)
+    em = fixtures["res32_eta"][1:-1].copy()
+    em[7] = np.nan
+    out = eng.residual(em)
+    assert np.isnan(out).any()
+    rc, x, iters, err = eng.adm_chen_batch(em, 1e-6, 10, 0.9, 3)
+    assert rc == 3                                     # SCFTB_ERR_NAN
+    eng.bind_global()
+    L = sb.lib()
+    x = em.copy()
+    assert L.scftb_adm_chen(L.scftb_callback_c0, x.ctypes.data_as(_dp), 1e-6, 10, 31, 0.9, 3, 0) == 3
+    eng.close()
+
+
+def test_callback_without_bound_engine_sets_funcerr(sb):
+    L = sb.lib()
+    L.scftb_bind_global(None)
+    x, y = np.zeros(31), np.zeros(31)
+    L.scftb_callback_c0(31, x.ctypes.data_as(_dp), y.ctypes.data_as(_dp))
+    assert C.c_int.in_dll(L, "scftb_funcerr").value == 1
+    eng = sb.Engine(33, nsteps=16)
+    eng.bind_global()
+    assert C.c_int.in_dll(L, "scftb_funcerr").value == 0
+    eng.close()
+
+
+def test_mixer_window_limits(sb):
+    eng = sb.Engine(33, nsteps=16)
+    with pytest.raises(sb.ScftError, match="window"):
+        sb.AndersonBatch(eng, 1, nn=51)
+    m = sb.AndersonBatch(eng, 1, nn=0)                 # nn = 0: pure relaxation X += (1-lk) Y
+    m.reset(np.zeros(31))
+    m.iterate_device(0)
+    done, iters, err = m.status(0)
+    assert err[0] > 0
+    m.close(); eng.close()
