@@ -92,6 +92,9 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+_emit = None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -145,7 +148,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": value, "unit": "DOF-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "DOF-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(problems_per_gpu):
@@ -160,6 +163,11 @@ def workload_config(problems_per_gpu):
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON); anything libraries print (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda line: (real_stdout.write(json.dumps(line) + "\n"), real_stdout.flush())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -302,7 +310,7 @@ def main():
             v, dt = oracle_throughput(cnt, cores)
             line["cpu_baseline"] = {"value": v, "unit": "DOF-steps/s", "cores": cores, "kind": "port",
                                     "sample": f"first {cnt} problems of the sweep, oracle/scft_oracle.c, {dt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
