@@ -1,7 +1,8 @@
-mkdir -p gpurun_out
-for n in 8 4; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/bench_r1_${n}gpu.json 2> gpurun_out/bench_r1_${n}gpu.err
-cut -c1-260 gpurun_out/bench_r1_${n}gpu.json; tail -2 gpurun_out/bench_r1_${n}gpu.err
-done
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29540 tools/bench2d_multi.py 4095 4095 256 2>&1 | grep -E "world|Error|error" | tail -3
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 tests/mgpu_pcg2d.py 2>&1 | grep -E "MGPU|Error|error" | tail -3
+python - <<'PY'
+import numpy as np, scft_b200 as sb
+fx=np.load('tests/golden/ref_fixtures.npz')
+sb.write_solution('/tmp/N33.txt', float(fx['n33_error']), float(fx['n33_F']), fx['n33_x'], fx['n33_eta'])
+PY
+./scft_b200/lib/drivescft_b200 /tmp/N33.txt --flow dealii --scheme ie_rowscale --solver adm_chen --levels 6 --tol 1e-9 --outdir /tmp | grep -E "^flow|^level"
+./scft_b200/lib/drivescft_b200 /tmp/N33.txt --flow dealii --scheme ie --solver adm_chen --levels 6 --tol 1e-9 --outdir /tmp | grep -E "^flow|^level"
+python -m pytest tests/test_gpu_edge_cases.py -m gpu -q 2>&1 | tail -3

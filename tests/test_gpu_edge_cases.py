@@ -51,8 +51,8 @@ def test_nan_field_is_reported_not_fatal(sb, fixtures):
     em[7] = np.nan
     out = eng.residual(em)
     assert np.isnan(out).any()
-    rc, x, iters, err = eng.adm_chen_batch(em, 1e-6, 10, 0.9, 3)
-    assert rc == 3                                     # SCFTB_ERR_NAN
+    with pytest.raises(sb.ScftError, match="NaN"):      # SCFTB_ERR_NAN
+        eng.adm_chen_batch(em, 1e-6, 10, 0.9, 3)
     eng.bind_global()
     L = sb.lib()
     x = em.copy()
