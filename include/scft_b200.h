@@ -116,6 +116,12 @@ int scftb_adm(scftb_func f, double *x, int n, int *check, int maxits);
  * is evaluated as ONE batch of n residuals on the device. */
 int scftb_broydn(scftb_func f, double *x, int n, int *check, double *err, int *jc);
 
+/* broydn with EVERYTHING on the device: finite-difference Jacobian as one batched launch, Householder QR,
+ * Q^T, Givens rank-one updates, triangular solves and line-search vectors stay in HBM; the host steers with a
+ * few scalars per step.  Solves problem 0 of the engine, whose first N-2 problems must share its (tau, L, mesh)
+ * (scftb_set_problem(e, -1, ...)); x[N-2] host in/out; check / err / jc as scftb_broydn. */
+int scftb_broydn_device(scftb_engine *e, double *x, int *check, double *err, int *jc);
+
 /* Device-resident batched Anderson mixing (adm_chen semantics) on the engine's problems:
  * x[nprob][N-2] host in/out.  All nprob problems iterate in lock-step, each with its own
  * history, Gram matrix, gaussj solve and relaxation; nothing but the per-problem error norms

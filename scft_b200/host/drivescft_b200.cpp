@@ -48,7 +48,7 @@ int main(int argc, char **argv) {
   }
   if (input.empty()) {
     fprintf(stderr, "usage: drivescft_b200 <N=33_for_read.txt | Exp_m32_n2048_IE.res> [--flow dealii|1dfem] "
-                    "[--scheme irk4|ie|ie_rowscale] [--solver broydn|adm_chen] [--levels K] [--nsteps n] [--tol t]\n");
+                    "[--scheme irk4|ie|ie_rowscale] [--solver broydn|broydn_dev|adm_chen] [--levels K] [--nsteps n] [--tol t]\n");
     return 2;
   }
   int scheme = scheme_s == "irk4" ? SCFTB_IRK4_CONSISTENT : (scheme_s == "ie" ? SCFTB_IE_CONSISTENT : SCFTB_IE_ROWSCALE);
@@ -85,6 +85,10 @@ int main(int argc, char **argv) {
       double err = tol;
       int jc = 0;
       rc = scftb_broydn(scftb_callback_c0, xm.data(), n, &check, &err, &jc);
+    } else if (solver == "broydn_dev") {   // the same iteration with Jacobian, QR and updates resident on the device
+      double err = tol;
+      int jc = 0;
+      rc = scftb_broydn_device(e, xm.data(), &check, &err, &jc);
     } else {  // staged schedule of drivescft.cc:294-298
       const double st[5][4] = {{1e-1, 200, 0.99, 2}, {1e-3, 300, 0.9, 3}, {1e-7, 800, 0.9, 15}, {1e-7, 1000, 0.9, 30},
                                {1e-7, 10000, 0.1, 50}};
