@@ -1,8 +1,5 @@
-timeout 500 python -m pytest tests/test_gpu_broyden_device.py -m gpu -q --tb=short 2>&1 | grep -E "^E  |passed|failed|Error" | cut -c1-220 | head -10
-python - <<'PY'
-import numpy as np, scft_b200 as sb
-fx=np.load('tests/golden/ref_fixtures.npz')
-sb.write_solution('/tmp/N33.txt', float(fx['n33_error']), float(fx['n33_F']), fx['n33_x'], fx['n33_eta'])
-PY
-./scft_b200/lib/drivescft_b200 /tmp/N33.txt --flow dealii --scheme ie_rowscale --solver broydn_dev --levels 6 --tol 1e-9 --outdir /tmp | grep -E "^flow|^level"
-./scft_b200/lib/drivescft_b200 /tmp/N33.txt --flow dealii --scheme ie --solver broydn_dev --levels 6 --tol 1e-9 --outdir /tmp | grep -E "^flow|^level"
+python -m pytest tests/test_gpu_pcg2d.py -m gpu -q 2>&1 | tail -2
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_pcg2d.py p2p 2>&1 | grep -E "^rank|MGPU|ScftError" | tail -12
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tools/bench2d_multi.py 1023 1023 256 p2p 2>&1 | grep -E "^world|ScftError" | tail -3
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29535 tools/bench2d_multi.py 255 255 2048 p2p 2>&1 | grep -E "^world|ScftError" | tail -3
+python tools/bench2d.py 255 255 2048 2>&1 | tail -1

@@ -186,6 +186,14 @@ int scftb2d_rows(scftb2d_engine *e, int *row0, int *nrows);
 int scftb2d_residual(scftb2d_engine *e, const double *eta, double *out);
 int scftb2d_get_phi(scftb2d_engine *e, double *phi /* nrows */);
 int scftb2d_get_stats(scftb2d_engine *e, long long *cg_iterations, double *march_ms);
+/* Peer-memory version of the exchange (one box, NVLink): every rank exports the cudaIpc handle (64 bytes) of its
+ * exchange buffer, the handles of all ranks are gathered (e.g. torch.distributed.all_gather) and attached; from then
+ * on scftb2d_residual runs the whole march as ONE persistent kernel per rank that stores halo columns straight into
+ * the neighbours' vectors and all-reduces the dot products through peer-mapped slots. */
+int scftb2d_p2p_handle(scftb2d_engine *e, char *handle64);
+int scftb2d_p2p_attach(scftb2d_engine *e, const char *handles /* world x 64 bytes */);
+/* unmap the peers; call on every rank and synchronise the ranks BEFORE scftb2d_destroy frees the exported memory */
+int scftb2d_p2p_detach(scftb2d_engine *e);
 /* CSR view (global column indices) of this rank's rows of T = A + ds(B+C) and A after the last assembly:
  * rowptr[nrows+1], colind/valT/valA[<= 9*nrows] */
 int scftb2d_export_csr(scftb2d_engine *e, int *rowptr, int *colind, double *valT, double *valA);

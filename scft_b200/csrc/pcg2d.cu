@@ -198,14 +198,24 @@ __device__ Part step_begin(const Sys2D &S, const Vec2D &V, int tid, int nthreads
   return acc;
 }
 
+// entry `c` (local index incl. halo offset) of a vector with halos; PEER: halo entries are written by another GPU
+// and must not be served from this SM's L1
+template <bool PEER>
+__device__ __forceinline__ double gather(const double *v, int c, const Sys2D &S) {
+  const int o = c - S.halo;
+  if (PEER && (o < 0 || o >= S.nrows)) return __ldcv(v + o);
+  return v[o];
+}
+
 // s = T z; partial sums gamma = r.z, delta = z.s, rr = r.r
+template <bool PEER = false>
 __device__ Part cg_spmv(const Sys2D &S, const Vec2D &V, int tid, int nthreads) {
   Part acc = {0, 0, 0, 0};
   for (int i = tid; i < S.nslices * 32; i += nthreads) {
     if (i >= S.nrows) continue;
     double sv = 0.0;
 #pragma unroll
-    for (int k = 0; k < SLOTS; k++) sv = fma(S.valT[sell(i, k)], V.z[S.col[sell(i, k)] - S.halo], sv);
+    for (int k = 0; k < SLOTS; k++) sv = fma(S.valT[sell(i, k)], gather<PEER>(V.z, S.col[sell(i, k)], S), sv);
     V.s[i] = sv;
     const double r = V.r[i], z = V.z[i];
     acc.a = fma(r, z, acc.a); acc.b = fma(z, sv, acc.b); acc.c = fma(r, r, acc.c);
@@ -290,6 +300,172 @@ __global__ void __launch_bounds__(TPB2) march2d_persistent_kernel(March2D M) {
     grid.sync();
   }
   if (tid == 0) *M.iters = iters;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi GPU, peer-memory version: ONE persistent cooperative kernel per rank for the whole march.  Halo
+// columns are stored straight into the neighbours' vectors over NVLink by the threads that produce them,
+// and the dot products are all-reduced through peer-mapped slots: compute and exchange live in the same
+// kernel, nothing is launched per iteration.  (cudaIpc handles of the exchange buffers travel through
+// torch.distributed; see scftb2d_p2p_handle / scftb2d_p2p_attach.)
+typedef unsigned long long ull;
+struct P2P {
+  int rank, world;
+  double *const *peers;      // [world] base of every rank's exchange buffer (own entry = local pointer)
+  size_t off_q, off_z;       // offsets (doubles) of the q / z vectors (halo-left start) inside an exchange buffer
+  size_t off_red;            // [2][world][4] reduction slots
+  size_t off_flag;           // ull flags: [0] left-in, [1] right-in, [2 + par*world + r] reduction arrivals
+  int nrows_left;            // owned rows of the left neighbour
+  long long timeout;         // cycles
+  volatile long long *dbg;   // host-mapped: [0] stage of a timed-out wait, [1] expected seq, [2] seen value, [3] block
+};
+
+__device__ __forceinline__ void wait_flag(const volatile ull *f, ull seq, const P2P &X, int stage) {
+  const long long t0 = clock64();
+  while (*f < seq)
+    if (clock64() - t0 > X.timeout) {   // a peer never arrived: abort this kernel instead of hanging the GPU
+      X.dbg[0] = stage; X.dbg[1] = (long long)seq; X.dbg[2] = (long long)*f; X.dbg[3] = blockIdx.x;
+      __threadfence_system();
+      __trap();
+    }
+}
+
+// boundary entries of an owned vector go straight into the neighbours' halo regions
+__device__ __forceinline__ bool push_boundary(const Sys2D &S, const P2P &X, size_t off_vec, int i, double v) {
+  bool pushed = false;
+  if (X.rank > 0 && i < S.halo) { X.peers[X.rank - 1][off_vec + S.halo + X.nrows_left + i] = v; pushed = true; }
+  if (X.rank + 1 < X.world && i >= S.nrows - S.halo) { X.peers[X.rank + 1][off_vec + (i - (S.nrows - S.halo))] = v; pushed = true; }
+  return pushed;
+}
+
+// after a grid barrier that follows the pushes: raise the neighbours' flags, wait for ours, drop stale L1 lines
+__device__ void halo_sync(const P2P &X, ull seq, cg::grid_group &grid) {
+  ull *myflags = (ull *)(X.peers[X.rank] + X.off_flag);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    if (X.rank > 0) ((volatile ull *)(X.peers[X.rank - 1] + X.off_flag))[1] = seq;
+    if (X.rank + 1 < X.world) ((volatile ull *)(X.peers[X.rank + 1] + X.off_flag))[0] = seq;
+  }
+  if (threadIdx.x == 0) {
+    if (X.rank > 0) wait_flag(myflags + 0, seq, X, 1);
+    if (X.rank + 1 < X.world) wait_flag(myflags + 1, seq, X, 2);
+    __threadfence_system();   // acquire
+  }
+  __syncthreads();   // halo entries are read with ld.cv (gather<true>), so no L1 invalidation is needed here
+}
+
+// all-reduce of the block partials over the ranks; every block of every rank returns the same sums
+__device__ Part allreduce_partials(const P2P &X, const double *partial, int nblocks, ull rseq, cg::grid_group &grid) {
+  const int par = (int)(rseq & 1);
+  if (blockIdx.x == 0) {
+    Part t = reduce_partials(partial, nblocks);
+    if (threadIdx.x < X.world) {
+      double *slot = X.peers[threadIdx.x] + X.off_red + (size_t)(par * X.world + X.rank) * 4;
+      slot[0] = t.a; slot[1] = t.b; slot[2] = t.c; slot[3] = t.d;
+      __threadfence_system();
+      ((volatile ull *)(X.peers[threadIdx.x] + X.off_flag))[2 + par * X.world + X.rank] = rseq;
+    }
+  }
+  __shared__ double tot[4];
+  if (threadIdx.x == 0) {
+    const volatile ull *fl = (const volatile ull *)(X.peers[X.rank] + X.off_flag) + 2 + par * X.world;
+    const volatile double *sl = X.peers[X.rank] + X.off_red + (size_t)par * X.world * 4;
+    double a = 0, b = 0, c = 0, d = 0;
+    for (int r = 0; r < X.world; r++) {   // fixed rank order: identical result everywhere
+      wait_flag(fl + r, rseq, X, 10 + r);
+      __threadfence_system();   // acquire: the slot values are read after the flag
+      a += sl[4 * r]; b += sl[4 * r + 1]; c += sl[4 * r + 2]; d += sl[4 * r + 3];
+    }
+    tot[0] = a; tot[1] = b; tot[2] = c; tot[3] = d;
+  }
+  __syncthreads();
+  Part t = {tot[0], tot[1], tot[2], tot[3]};
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(TPB2) march2d_p2p_kernel(March2D M, P2P X, ull seq0, ull rseq0) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const Sys2D &S = M.S; const Vec2D &V = M.V;
+  ull seq = seq0, rseq = rseq0;   // halo / reduction sequence numbers continue across launches
+  int slot = 0;
+  long long iters = 0;
+  for (int i = tid; i < S.nrows; i += nthreads) {
+    const int ix = (S.row0 + i) / S.nyp;
+    const double q0 = (ix == 0 || ix == S.nx) ? 0.0 : 1.0;
+    V.q[i] = q0; M.phi[i] = 0.0; M.hist[i] = q0;
+    if (push_boundary(S, X, X.off_q, i, q0)) __threadfence_system();   // peer stores ordered before the flag
+  }
+  grid.sync();
+  halo_sync(X, ++seq, grid);
+  for (int j = 1; j <= M.nsteps; j++) {
+    // b = A q, x = q, r = b - T x, z = D^-1 r (boundary z goes to the neighbours at once)
+    Part pb = {0, 0, 0, 0};
+    for (int i = tid; i < S.nslices * 32; i += nthreads) {
+      if (i >= S.nrows) continue;
+      double bq = 0.0, tq = 0.0;
+#pragma unroll
+      for (int k = 0; k < SLOTS; k++) {
+        const double qv = gather<true>(V.q, S.col[sell(i, k)], S);
+        bq = fma(S.valA[sell(i, k)], qv, bq);
+        tq = fma(S.valT[sell(i, k)], qv, tq);
+      }
+      const double r = bq - tq, z = S.dinv[i] * r;
+      V.b[i] = bq; V.x[i] = V.q[i]; V.r[i] = r; V.z[i] = z; V.p[i] = 0.0; V.w[i] = 0.0;
+      if (push_boundary(S, X, X.off_z, i, z)) __threadfence_system();
+      pb.d = fma(bq, bq, pb.d);
+    }
+    block_partials(pb, M.R.partial + ((size_t)slot * gridDim.x + blockIdx.x) * 4);
+    grid.sync();
+    const double bb = allreduce_partials(X, M.R.partial + (size_t)slot * gridDim.x * 4, gridDim.x, ++rseq, grid).d;
+    slot ^= 1;
+    halo_sync(X, ++seq, grid);
+    const double tol2 = M.rtol * M.rtol * bb;
+    double gamma_old = 1.0, alpha_old = 1.0;
+    for (int it = 0; it < M.maxit; it++) {
+      Part pa = cg_spmv<true>(S, V, tid, nthreads);
+      block_partials(pa, M.R.partial + ((size_t)slot * gridDim.x + blockIdx.x) * 4);
+      grid.sync();
+      const Part t = allreduce_partials(X, M.R.partial + (size_t)slot * gridDim.x * 4, gridDim.x, ++rseq, grid);
+      slot ^= 1;
+      if (t.c <= tol2) break;
+      const double beta = (it == 0) ? 0.0 : t.a / gamma_old;
+      const double alpha = (it == 0) ? t.a / t.b : t.a / (t.b - beta * t.a / alpha_old);
+      for (int i = tid; i < S.nrows; i += nthreads) {   // cg_update + push of the new boundary z
+        const double p = fma(beta, V.p[i], V.z[i]), w = fma(beta, V.w[i], V.s[i]);
+        V.p[i] = p; V.w[i] = w;
+        V.x[i] = fma(alpha, p, V.x[i]);
+        const double r = fma(-alpha, w, V.r[i]);
+        const double z = S.dinv[i] * r;
+        V.r[i] = r; V.z[i] = z;
+        if (push_boundary(S, X, X.off_z, i, z)) __threadfence_system();
+      }
+      gamma_old = t.a; alpha_old = alpha;
+      iters++;
+      grid.sync();
+      halo_sync(X, ++seq, grid);
+    }
+    // step end: q = x (+ push), history, fused quadrature
+    {
+      const int n = M.nsteps;
+      const bool pairing = 2 * j > n;
+      const double wj = (2 * j >= n) ? M.wq[j] : 0.0;
+      for (int i = tid; i < S.nrows; i += nthreads) {
+        const double qv = V.x[i];
+        V.q[i] = qv;
+        if (push_boundary(S, X, X.off_q, i, qv)) __threadfence_system();
+        if (M.store_full || 2 * j < n) M.hist[(size_t)j * S.nrows + i] = qv;
+        if (2 * j >= n) {
+          const double qo = pairing ? M.hist[(size_t)(n - j) * S.nrows + i] : qv;
+          M.phi[i] = fma(wj * qv, qo, M.phi[i]);
+        }
+      }
+    }
+    grid.sync();
+    halo_sync(X, ++seq, grid);
+  }
+  if (tid == 0) { *M.iters = iters; M.R.scal[30] = (double)seq; M.R.scal[31] = (double)rseq; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -382,6 +558,11 @@ constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;   // ncclFloat64, ncclSum (nccl.h)
 
 }  // namespace scftb
 
+// exchange buffers exported over cudaIpc are recycled, never freed: a peer process may still hold a mapping, and
+// re-exporting memory freed and re-allocated inside the same CUDA memory block is not reliable
+struct XchgArena { int device; double *base; size_t doubles; bool busy; };
+static std::vector<XchgArena> g_arenas;
+
 struct scftb2d_engine {
   scftb2d_config cfg;
   int nyp, ndof, ix0, ix1, nrows, halo, nslices, grid_persist, grid_step;
@@ -394,6 +575,15 @@ struct scftb2d_engine {
   double last_ms;
   cudaGraphExec_t graph_exec;
   double *h_flag;   // pinned
+  // peer-memory exchange (world > 1)
+  double *d_xchg;
+  size_t xchg_doubles;
+  P2P p2p;
+  bool attached;
+  std::vector<void *> opened;
+  double **d_peers;
+  unsigned long long seq, rseq;
+  volatile long long *h_dbg;
 };
 
 #define NK(call)                                                                                              \
@@ -416,11 +606,13 @@ int scftb2d_destroy(scftb2d_engine *e) {
   if (!e) return SCFTB_OK;
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
+  for (void *p : e->opened) cudaIpcCloseMemHandle(p);
+  for (auto &a : g_arenas) if (a.base == e->d_xchg) a.busy = false;
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->h_flag) cudaFreeHost(e->h_flag);
   if (e->comm) g_nccl.CommDestroy(e->comm);
   for (void *p : {(void *)e->M.S.col, (void *)e->M.S.valT, (void *)e->M.S.valA, (void *)e->M.S.dinv, (void *)e->d_eta,
-                  (void *)e->d_qbuf, (void *)e->d_zbuf, (void *)e->M.V.x, (void *)e->M.V.r, (void *)e->M.V.s, (void *)e->M.V.p,
+                  (void *)e->d_peers, (void *)e->M.V.x, (void *)e->M.V.r, (void *)e->M.V.s, (void *)e->M.V.p,
                   (void *)e->M.V.w, (void *)e->M.V.b, (void *)e->M.R.partial, (void *)e->M.R.scal, (void *)e->M.hist,
                   (void *)e->M.phi, (void *)e->M.iters, (void *)e->d_out, (void *)e->d_f0, (void *)e->M.wq})
     if (p) cudaFree(p);
@@ -436,7 +628,7 @@ int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_en
   if (cfg->world > 1 && (cfg->nx + 1) / cfg->world < 2) return fail(SCFTB_ERR_ARG, "too few node columns per rank");
   scftb2d_engine *e = new scftb2d_engine();
   memset(&e->M, 0, sizeof(e->M));
-  e->cfg = *cfg; e->comm = nullptr; e->d_eta = e->d_qbuf = e->d_zbuf = e->d_out = e->d_f0 = nullptr; e->last_iters = 0; e->last_ms = 0; e->graph_exec = nullptr; e->h_flag = nullptr;
+  e->cfg = *cfg; e->comm = nullptr; e->d_eta = e->d_qbuf = e->d_zbuf = e->d_out = e->d_f0 = nullptr; e->last_iters = 0; e->last_ms = 0; e->graph_exec = nullptr; e->h_flag = nullptr; e->d_xchg = nullptr; e->attached = false; e->d_peers = nullptr; e->seq = 0; e->rseq = 0;
   const int nx = cfg->nx, ny = cfg->ny, nyp = ny + 1, n = cfg->nsteps;
   e->nyp = nyp; e->ndof = (nx + 1) * nyp;
   // slab partition: node columns [ix0, ix1) (1-D slab along x, one node column of halo per neighbour)
@@ -467,10 +659,32 @@ int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_en
   CK2(cudaMalloc(&S.dinv, sizeof(double) * nr));
   CK2(cudaMalloc(&e->d_eta, sizeof(double) * e->ndof));
   S.eta = e->d_eta;
-  CK2(cudaMalloc(&e->d_qbuf, sizeof(double) * nh));
-  CK2(cudaMalloc(&e->d_zbuf, sizeof(double) * nh));
-  CK2(cudaMemset(e->d_qbuf, 0, sizeof(double) * nh));
-  CK2(cudaMemset(e->d_zbuf, 0, sizeof(double) * nh));
+  {  // one exportable allocation: q and z (with halos), the reduction slots and the flags
+    // the layout must be identical on every rank (peers address each other's buffers with their own offsets):
+    // size the vectors for the widest slab
+    const size_t nh_max = (size_t)((nx + 1 + cfg->world - 1) / cfg->world + 1) * nyp + 2 * (size_t)e->halo;
+    const size_t nhp = (nh_max + 15) / 16 * 16, red = (size_t)2 * cfg->world * 4, fl = (size_t)(2 + 2 * cfg->world + 14) / 16 * 16 + 16;
+    e->p2p.off_q = 0; e->p2p.off_z = nhp; e->p2p.off_red = 2 * nhp; e->p2p.off_flag = 2 * nhp + (red + 15) / 16 * 16;
+    e->xchg_doubles = e->p2p.off_flag + fl;
+    for (auto &a : g_arenas)
+      if (!a.busy && a.device == cfg->device && a.doubles >= e->xchg_doubles) { e->d_xchg = a.base; a.busy = true; break; }
+    if (!e->d_xchg) {
+      const size_t want = std::max(e->xchg_doubles, (size_t)1 << 20);
+      CK2(cudaMalloc(&e->d_xchg, sizeof(double) * want));
+      g_arenas.push_back({cfg->device, e->d_xchg, want, true});
+    }
+    CK2(cudaMemset(e->d_xchg, 0, sizeof(double) * e->xchg_doubles));
+    e->d_qbuf = e->d_xchg + e->p2p.off_q; e->d_zbuf = e->d_xchg + e->p2p.off_z;
+    e->p2p.rank = cfg->rank; e->p2p.world = cfg->world; e->p2p.peers = nullptr;
+    const int lx0 = cfg->rank > 0 ? (int)((long long)(nx + 1) * (cfg->rank - 1) / cfg->world) : 0;
+    e->p2p.nrows_left = cfg->rank > 0 ? (e->ix0 - lx0) * nyp : 0;
+    e->p2p.timeout = 6000000000LL;   // ~3 s of SM clocks
+    CK2(cudaHostAlloc((void **)&e->h_dbg, sizeof(long long) * 8, cudaHostAllocMapped));
+    memset((void *)e->h_dbg, 0, sizeof(long long) * 8);
+    long long *ddbg = nullptr;
+    CK2(cudaHostGetDevicePointer((void **)&ddbg, (void *)e->h_dbg, 0));
+    e->p2p.dbg = ddbg;
+  }
   Vec2D &V = e->M.V;
   V.q = e->d_qbuf + e->halo; V.z = e->d_zbuf + e->halo;
   for (double **p : {&V.x, &V.r, &V.s, &V.p, &V.w, &V.b}) CK2(cudaMalloc(p, sizeof(double) * nr));
@@ -490,8 +704,13 @@ int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_en
   int sms = 0, occ = 0;
   CK2(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
   CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march2d_persistent_kernel, TPB2, 0));
+  {
+    int occp = 0;
+    CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, march2d_p2p_kernel, TPB2, 0));
+    if (cfg->world > 1) occ = std::min(occ, occp);
+  }
   occ = std::max(1, std::min(occ, 4));
-  e->grid_persist = sms * occ;
+  e->grid_persist = std::max(1, std::min(sms * occ, (e->nrows + 4 * TPB2 - 1) / (4 * TPB2)));   // small meshes: fewer blocks, cheaper barriers
   int occ2 = 0;
   CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, spmv_kernel, TPB2, 0));
   e->grid_step = sms * std::max(1, std::min(occ2, 4));
@@ -508,7 +727,54 @@ int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_en
     int r = g_nccl.CommInitRank(&e->comm, cfg->world, id, cfg->rank);
     if (r != 0) { int rc = fail(SCFTB_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); scftb2d_destroy(e); return rc; }
   }
+  CK2(cudaDeviceSynchronize());   // the zeroed exchange buffer is in place before any peer can be told about it
   *out = e;
+  return SCFTB_OK;
+}
+
+// cudaIpc handle (64 bytes) of this rank's exchange buffer
+int scftb2d_p2p_handle(scftb2d_engine *e, char *handle64) {
+  if (!e || !handle64) return fail(SCFTB_ERR_ARG, "null argument");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, e->d_xchg));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return SCFTB_OK;
+}
+
+// handles: world x 64 bytes, entry r = scftb2d_p2p_handle of rank r.  From then on scftb2d_residual runs the
+// peer-memory persistent kernel instead of the NCCL path.
+int scftb2d_p2p_attach(scftb2d_engine *e, const char *handles) {
+  if (!e || !handles) return fail(SCFTB_ERR_ARG, "null argument");
+  if (e->cfg.world < 2) return fail(SCFTB_ERR_STATE, "p2p needs world > 1");
+  CK(cudaSetDevice(e->cfg.device));
+  std::vector<double *> peers(e->cfg.world, nullptr);
+  for (int r = 0; r < e->cfg.world; r++) {
+    if (r == e->cfg.rank) { peers[r] = e->d_xchg; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)64 * r, 64);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    e->opened.push_back(p);
+    peers[r] = (double *)p;
+  }
+  CK(cudaMalloc(&e->d_peers, sizeof(double *) * e->cfg.world));
+  CK(cudaMemcpy(e->d_peers, peers.data(), sizeof(double *) * e->cfg.world, cudaMemcpyHostToDevice));
+  e->p2p.peers = e->d_peers;
+  e->attached = true;
+  return SCFTB_OK;
+}
+
+// close the peer mappings (call on every rank, then synchronise the ranks, then destroy: exported memory must
+// not be freed while a peer still maps it)
+int scftb2d_p2p_detach(scftb2d_engine *e) {
+  if (!e) return fail(SCFTB_ERR_ARG, "null engine");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->stream));
+  for (void *p : e->opened) cudaIpcCloseMemHandle(p);
+  e->opened.clear();
+  e->attached = false;
   return SCFTB_OK;
 }
 
@@ -534,7 +800,23 @@ int scftb2d_residual(scftb2d_engine *e, const double *eta, double *out) {
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, st));
   March2D M = e->M;
-  if (e->cfg.world == 1) {
+  if (e->cfg.world > 1 && e->attached) {
+    P2P X = e->p2p;
+    unsigned long long s0 = e->seq, r0 = e->rseq;
+    void *args[] = {&M, &X, &s0, &r0};
+    CK(cudaLaunchCooperativeKernel((void *)march2d_p2p_kernel, dim3(e->grid_persist), dim3(TPB2), args, 0, st));
+    g_launches++;
+    double sq[2];
+    cudaError_t ce = cudaMemcpyAsync(sq, M.R.scal + 30, sizeof(double) * 2, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) {
+      char msg[256];
+      snprintf(msg, sizeof msg, "peer-memory march failed (%s); timed-out wait: stage %lld expected seq %lld saw %lld in block %lld (rank %d)",
+               cudaGetErrorString(ce), e->h_dbg[0], e->h_dbg[1], e->h_dbg[2], e->h_dbg[3], e->cfg.rank);
+      return fail(SCFTB_ERR_CUDA, msg);
+    }
+    e->seq = (unsigned long long)sq[0]; e->rseq = (unsigned long long)sq[1];
+  } else if (e->cfg.world == 1) {
     void *args[] = {&M};
     CK(cudaLaunchCooperativeKernel((void *)march2d_persistent_kernel, dim3(e->grid_persist), dim3(TPB2), args, 0, st));
     g_launches++;

@@ -48,7 +48,7 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
            "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_write_solution",
            "scftb_read_solution", "scftb_read_res", "scftb2d_nccl_unique_id", "scftb2d_create", "scftb2d_destroy",
-           "scftb2d_rows", "scftb2d_residual", "scftb2d_get_phi", "scftb2d_get_stats", "scftb2d_export_csr"]
+           "scftb2d_rows", "scftb2d_p2p_handle", "scftb2d_p2p_attach", "scftb2d_p2p_detach", "scftb2d_residual", "scftb2d_get_phi", "scftb2d_get_stats", "scftb2d_export_csr"]
 
 
 def lib():
@@ -99,6 +99,9 @@ def lib():
         L.scftb2d_create.argtypes = [C.POINTER(_Config2D), C.c_char_p, C.POINTER(C.c_void_p)]
         L.scftb2d_destroy.argtypes = [C.c_void_p]
         L.scftb2d_rows.argtypes = [C.c_void_p, _ip, _ip]
+        L.scftb2d_p2p_handle.argtypes = [C.c_void_p, C.c_char_p]
+        L.scftb2d_p2p_attach.argtypes = [C.c_void_p, C.c_char_p]
+        L.scftb2d_p2p_detach.argtypes = [C.c_void_p]
         L.scftb2d_residual.argtypes = [C.c_void_p, _dp, _dp]
         L.scftb2d_get_phi.argtypes = [C.c_void_p, _dp]
         L.scftb2d_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), _dp]
@@ -325,6 +328,18 @@ class Engine2D:
             self._h = None
 
     __del__ = close
+
+    def p2p_handle(self):
+        buf = C.create_string_buffer(64)
+        _chk(lib().scftb2d_p2p_handle(self._h, buf))
+        return buf.raw
+
+    def p2p_attach(self, handles):
+        """handles: bytes of length 64*world (rank order)"""
+        _chk(lib().scftb2d_p2p_attach(self._h, handles))
+
+    def p2p_detach(self):
+        _chk(lib().scftb2d_p2p_detach(self._h))
 
     def residual(self, eta):
         eta = np.ascontiguousarray(eta, dtype=np.float64)

@@ -20,6 +20,12 @@ eta_x = np.interp(x, fx["res1024_xl"] * L, fx["res1024_eta"])
 y = np.arange(ny + 1) / ny
 eta = (eta_x[:, None] * (1 + 0.1 * np.cos(2 * np.pi * y)[None, :])).ravel()
 eng = sb.Engine2D(nx, ny, L=L, Ly=L, nsteps=n, rtol=1e-12, device=local, rank=rank, world=world, nccl_id=bytes(idt.cpu().tolist()))
+if len(sys.argv) > 4 and sys.argv[4] == "p2p":
+    hb = torch.tensor(list(eng.p2p_handle()), dtype=torch.uint8, device="cuda")
+    allh = [torch.zeros_like(hb) for _ in range(world)]
+    dist.all_gather(allh, hb)
+    eng.p2p_attach(b"".join(bytes(h.cpu().tolist()) for h in allh))
+    dist.barrier()
 for rep in range(2):
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter(); out = eng.residual(eta); torch.cuda.synchronize(); wall = time.perf_counter() - t0
@@ -29,7 +35,10 @@ chk = torch.tensor([float(np.abs(out).sum())], device="cuda", dtype=torch.float6
 if rank == 0:
     ndof = (nx + 1) * (ny + 1)
     ms = float(t[0])
-    print(f"world {world}: mesh {nx}x{ny} ({ndof} DOFs), {n} steps: march {ms:.1f} ms, {it} CG iterations = {it/n:.1f}/step, "
+    print(f"world {world} [{sys.argv[4] if len(sys.argv) > 4 else 'nccl'}]: mesh {nx}x{ny} ({ndof} DOFs), {n} steps: march {ms:.1f} ms, {it} CG iterations = {it/n:.1f}/step, "
           f"{ms*1e3/it:.2f} us/iteration, {ndof*n/(ms*1e-3):.3e} DOF-steps/s, sum|out| {float(chk[0]):.12e}", flush=True)
+if len(sys.argv) > 4 and sys.argv[4] == "p2p":
+    eng.p2p_detach()
+dist.barrier()
 eng.close()
 dist.destroy_process_group()
