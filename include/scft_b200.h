@@ -152,6 +152,10 @@ int scftb_spline(const double *x, const double *y, const double *xp, double *yp,
 /* refine_mesh (scft.cc:132-169): every cell cut in x, N -> 2N-1 nodes; the interior field is carried over by a
  * not-a-knot spline through the old interior nodes.  x_new[2N-1], eta_mid_new[2N-3]. */
 int scftb_refine_mesh(int N, const double *x, const double *eta_mid, double *x_new, double *eta_mid_new);
+/* refine_mesh.m:6-30 (MATLAB prototype): cut the cells whose |d eta/dx| is >= factor x the median (the prototype
+ * uses 10) and the two wall cells; not-a-knot transfer.  *N_new <= 2N-1; buffers sized for 2N-1 / 2N-3. */
+int scftb_refine_mesh_adaptive(int N, const double *x, const double *eta_mid, double factor, int *N_new, double *x_new,
+                               double *eta_mid_new);
 /* solution_yita_1D_N=<N>.txt writer (scft.cc:319-337) and reader (read_yita_middle_1D, scft_util.cc:13-41) */
 int scftb_write_solution(const char *path, int N, double err, double F, const double *x, const double *eta_full);
 int scftb_read_solution(const char *path, int *N, double *x, double *eta, int capacity);

@@ -209,10 +209,14 @@ __device__ __forceinline__ double gather(const double *v, int c, const Sys2D &S)
 
 // s = T z; partial sums gamma = r.z, delta = z.s, rr = r.r
 template <bool PEER = false>
-__device__ Part cg_spmv(const Sys2D &S, const Vec2D &V, int tid, int nthreads) {
+__device__ Part cg_spmv(const Sys2D &S, const Vec2D &V, int tid, int nthreads, int phase = 0) {
   Part acc = {0, 0, 0, 0};
   for (int i = tid; i < S.nslices * 32; i += nthreads) {
     if (i >= S.nrows) continue;
+    if (phase != 0) {   // rows of the first / last owned node column are the only ones that read halo entries
+      const bool edge = (i < S.halo) || (i >= S.nrows - S.halo);
+      if (edge != (phase == 2)) continue;
+    }
     double sv = 0.0;
 #pragma unroll
     for (int k = 0; k < SLOTS; k++) sv = fma(S.valT[sell(i, k)], gather<PEER>(V.z, S.col[sell(i, k)], S), sv);
@@ -320,11 +324,25 @@ struct P2P {
   volatile long long *dbg;   // host-mapped: [0] stage of a timed-out wait, [1] expected seq, [2] seen value, [3] block
 };
 
-__device__ __forceinline__ void wait_flag(const volatile ull *f, ull seq, const P2P &X, int stage) {
+__device__ __forceinline__ ull ld_acquire_sys(const ull *p) {
+  ull v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(ull *p, ull v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ ull ld_acquire_gpu(const ull *p) {
+  ull v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(ull *p, ull v) { asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+// spin (acquire, system scope) until a flag written by a peer GPU reaches seq
+__device__ __forceinline__ void wait_flag(const ull *f, ull seq, const P2P &X, int stage) {
   const long long t0 = clock64();
-  while (*f < seq)
+  while (ld_acquire_sys(f) < seq)
     if (clock64() - t0 > X.timeout) {   // a peer never arrived: abort this kernel instead of hanging the GPU
-      X.dbg[0] = stage; X.dbg[1] = (long long)seq; X.dbg[2] = (long long)*f; X.dbg[3] = blockIdx.x;
+      X.dbg[0] = stage; X.dbg[1] = (long long)seq; X.dbg[2] = (long long)ld_acquire_sys(f); X.dbg[3] = blockIdx.x;
       __threadfence_system();
       __trap();
     }
@@ -338,45 +356,57 @@ __device__ __forceinline__ bool push_boundary(const Sys2D &S, const P2P &X, size
   return pushed;
 }
 
-// after a grid barrier that follows the pushes: raise the neighbours' flags, wait for ours, drop stale L1 lines
-__device__ void halo_sync(const P2P &X, ull seq, cg::grid_group &grid) {
-  ull *myflags = (ull *)(X.peers[X.rank] + X.off_flag);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    __threadfence_system();
-    if (X.rank > 0) ((volatile ull *)(X.peers[X.rank - 1] + X.off_flag))[1] = seq;
-    if (X.rank + 1 < X.world) ((volatile ull *)(X.peers[X.rank + 1] + X.off_flag))[0] = seq;
+// after a grid barrier that follows the pushes: raise the neighbours' flags ...
+__device__ __forceinline__ void halo_signal(const P2P &X, ull seq) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // the pushing threads fenced (system scope) before the grid barrier
+    if (X.rank > 0) st_release_sys((ull *)(X.peers[X.rank - 1] + X.off_flag) + 1, seq);
+    if (X.rank + 1 < X.world) st_release_sys((ull *)(X.peers[X.rank + 1] + X.off_flag) + 0, seq);
   }
+}
+// ... and, as late as possible (only the rows next to a slab boundary read halo entries), wait for ours
+__device__ void halo_wait(const P2P &X, ull seq) {
+  ull *myflags = (ull *)(X.peers[X.rank] + X.off_flag);
   if (threadIdx.x == 0) {
     if (X.rank > 0) wait_flag(myflags + 0, seq, X, 1);
     if (X.rank + 1 < X.world) wait_flag(myflags + 1, seq, X, 2);
-    __threadfence_system();   // acquire
   }
   __syncthreads();   // halo entries are read with ld.cv (gather<true>), so no L1 invalidation is needed here
 }
 
-// all-reduce of the block partials over the ranks; every block of every rank returns the same sums
+// all-reduce of the block partials over the ranks; every block of every rank returns the same sums.
+// Block 0 folds the partials, stores them into every peer's slot (release, system scope), gathers the peers'
+// contributions in rank order and publishes the totals to the other blocks through a local flag (gpu scope):
+// only one block per GPU polls peer-written memory.
 __device__ Part allreduce_partials(const P2P &X, const double *partial, int nblocks, ull rseq, cg::grid_group &grid) {
   const int par = (int)(rseq & 1);
+  double *self = X.peers[X.rank];
+  ull *flags = (ull *)(self + X.off_flag);
+  double *gsum = self + X.off_red + (size_t)2 * X.world * 4 + par * 4;   // local totals [2][4]
+  ull *gready = flags + 2 + 2 * X.world;                                  // local "totals ready" sequence number
+  __shared__ double tot[4];
   if (blockIdx.x == 0) {
     Part t = reduce_partials(partial, nblocks);
     if (threadIdx.x < X.world) {
       double *slot = X.peers[threadIdx.x] + X.off_red + (size_t)(par * X.world + X.rank) * 4;
       slot[0] = t.a; slot[1] = t.b; slot[2] = t.c; slot[3] = t.d;
-      __threadfence_system();
-      ((volatile ull *)(X.peers[threadIdx.x] + X.off_flag))[2 + par * X.world + X.rank] = rseq;
+      st_release_sys((ull *)(X.peers[threadIdx.x] + X.off_flag) + 2 + par * X.world + X.rank, rseq);
     }
-  }
-  __shared__ double tot[4];
-  if (threadIdx.x == 0) {
-    const volatile ull *fl = (const volatile ull *)(X.peers[X.rank] + X.off_flag) + 2 + par * X.world;
-    const volatile double *sl = X.peers[X.rank] + X.off_red + (size_t)par * X.world * 4;
-    double a = 0, b = 0, c = 0, d = 0;
-    for (int r = 0; r < X.world; r++) {   // fixed rank order: identical result everywhere
-      wait_flag(fl + r, rseq, X, 10 + r);
-      __threadfence_system();   // acquire: the slot values are read after the flag
-      a += sl[4 * r]; b += sl[4 * r + 1]; c += sl[4 * r + 2]; d += sl[4 * r + 3];
+    if (threadIdx.x == 0) {
+      const double *sl = self + X.off_red + (size_t)par * X.world * 4;
+      double a = 0, b = 0, c = 0, d = 0;
+      for (int r = 0; r < X.world; r++) {   // fixed rank order: identical result everywhere
+        wait_flag(flags + 2 + par * X.world + r, rseq, X, 10 + r);
+        a += __ldcv(sl + 4 * r); b += __ldcv(sl + 4 * r + 1); c += __ldcv(sl + 4 * r + 2); d += __ldcv(sl + 4 * r + 3);
+      }
+      gsum[0] = a; gsum[1] = b; gsum[2] = c; gsum[3] = d;
+      st_release_gpu(gready, rseq);
+      tot[0] = a; tot[1] = b; tot[2] = c; tot[3] = d;
     }
-    tot[0] = a; tot[1] = b; tot[2] = c; tot[3] = d;
+  } else if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(gready) < rseq)
+      if (clock64() - t0 > 2 * X.timeout) { X.dbg[0] = 99; X.dbg[1] = (long long)rseq; X.dbg[3] = blockIdx.x; __threadfence_system(); __trap(); }
+    tot[0] = __ldcg(gsum); tot[1] = __ldcg(gsum + 1); tot[2] = __ldcg(gsum + 2); tot[3] = __ldcg(gsum + 3);
   }
   __syncthreads();
   Part t = {tot[0], tot[1], tot[2], tot[3]};
@@ -398,7 +428,8 @@ __global__ void __launch_bounds__(TPB2) march2d_p2p_kernel(March2D M, P2P X, ull
     if (push_boundary(S, X, X.off_q, i, q0)) __threadfence_system();   // peer stores ordered before the flag
   }
   grid.sync();
-  halo_sync(X, ++seq, grid);
+  halo_signal(X, ++seq);
+  halo_wait(X, seq);
   for (int j = 1; j <= M.nsteps; j++) {
     // b = A q, x = q, r = b - T x, z = D^-1 r (boundary z goes to the neighbours at once)
     Part pb = {0, 0, 0, 0};
@@ -420,11 +451,15 @@ __global__ void __launch_bounds__(TPB2) march2d_p2p_kernel(March2D M, P2P X, ull
     grid.sync();
     const double bb = allreduce_partials(X, M.R.partial + (size_t)slot * gridDim.x * 4, gridDim.x, ++rseq, grid).d;
     slot ^= 1;
-    halo_sync(X, ++seq, grid);
+    halo_signal(X, ++seq);   // z of step_begin was pushed before the barrier above
     const double tol2 = M.rtol * M.rtol * bb;
     double gamma_old = 1.0, alpha_old = 1.0;
     for (int it = 0; it < M.maxit; it++) {
-      Part pa = cg_spmv<true>(S, V, tid, nthreads);
+      // rows that touch no halo entry first; the neighbours' columns are awaited only for the two boundary columns
+      Part pa = cg_spmv<true>(S, V, tid, nthreads, 1);
+      halo_wait(X, seq);
+      Part pb2 = cg_spmv<true>(S, V, tid, nthreads, 2);
+      pa.a += pb2.a; pa.b += pb2.b; pa.c += pb2.c;
       block_partials(pa, M.R.partial + ((size_t)slot * gridDim.x + blockIdx.x) * 4);
       grid.sync();
       const Part t = allreduce_partials(X, M.R.partial + (size_t)slot * gridDim.x * 4, gridDim.x, ++rseq, grid);
@@ -444,7 +479,7 @@ __global__ void __launch_bounds__(TPB2) march2d_p2p_kernel(March2D M, P2P X, ull
       gamma_old = t.a; alpha_old = alpha;
       iters++;
       grid.sync();
-      halo_sync(X, ++seq, grid);
+      halo_signal(X, ++seq);
     }
     // step end: q = x (+ push), history, fused quadrature
     {
@@ -463,7 +498,8 @@ __global__ void __launch_bounds__(TPB2) march2d_p2p_kernel(March2D M, P2P X, ull
       }
     }
     grid.sync();
-    halo_sync(X, ++seq, grid);
+    halo_signal(X, ++seq);
+    halo_wait(X, seq);
   }
   if (tid == 0) { *M.iters = iters; M.R.scal[30] = (double)seq; M.R.scal[31] = (double)rseq; }
 }
@@ -663,7 +699,7 @@ int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_en
     // the layout must be identical on every rank (peers address each other's buffers with their own offsets):
     // size the vectors for the widest slab
     const size_t nh_max = (size_t)((nx + 1 + cfg->world - 1) / cfg->world + 1) * nyp + 2 * (size_t)e->halo;
-    const size_t nhp = (nh_max + 15) / 16 * 16, red = (size_t)2 * cfg->world * 4, fl = (size_t)(2 + 2 * cfg->world + 14) / 16 * 16 + 16;
+    const size_t nhp = (nh_max + 15) / 16 * 16, red = (size_t)2 * cfg->world * 4 + 8, fl = (size_t)(3 + 2 * cfg->world + 14) / 16 * 16 + 16;
     e->p2p.off_q = 0; e->p2p.off_z = nhp; e->p2p.off_red = 2 * nhp; e->p2p.off_flag = 2 * nhp + (red + 15) / 16 * 16;
     e->xchg_doubles = e->p2p.off_flag + fl;
     for (auto &a : g_arenas)

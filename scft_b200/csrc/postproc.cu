@@ -5,6 +5,7 @@
 //     (scft.cc:132-169), and the refinement-level bookkeeping of the driver loop (drivescft.cc:291-322)
 //   * the reference's result-file format: writer (scft.cc:319-337) and reader (scft_util.cc:13-41),
 //     and the .res reader of 1D_FEM.c:322-342
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -93,6 +94,33 @@ int scftb_refine_mesh(int N, const double *x, const double *eta_mid, double *x_n
   for (int i = 0; i < N; i++) x_new[2 * i] = x[i];
   for (int i = 0; i + 1 < N; i++) x_new[2 * i + 1] = 0.5 * (x[i] + x[i + 1]);
   return scftb_spline(x + 1, eta_mid, x_new + 1, eta_mid_new, N - 2, Nn - 2, 1, 0.0);
+}
+
+// gradient-based local bisection of Matlab_files/refine_mesh.m:6-30 (the non-uniform-mesh variant): a cell is cut
+// when |d eta / dx| across it is >= factor * median over the cells (the two wall cells, whose outer value is
+// unknown (Inf in the prototype), are always cut); the field moves to the new interior nodes by the not-a-knot
+// spline (refine_mesh.m:41).  Returns the new node count in *N_new; x_new / eta_mid_new need room for 2N-1 / 2N-3.
+int scftb_refine_mesh_adaptive(int N, const double *x, const double *eta_mid, double factor, int *N_new, double *x_new,
+                               double *eta_mid_new) {
+  if (N < 6 || !x || !eta_mid || !N_new || !x_new || !eta_mid_new) return fail(SCFTB_ERR_ARG, "refine: bad argument");
+  const int cells = N - 1;
+  std::vector<double> err(cells);
+  for (int c = 0; c < cells; c++) {
+    if (c == 0 || c == cells - 1) { err[c] = INFINITY; continue; }   // solution = [Inf; x_old; Inf]
+    err[c] = std::fabs((eta_mid[c] - eta_mid[c - 1]) / (x[c + 1] - x[c]));
+  }
+  std::vector<double> sorted(err);
+  std::sort(sorted.begin(), sorted.end());
+  const double med = (cells % 2) ? sorted[cells / 2] : 0.5 * (sorted[cells / 2 - 1] + sorted[cells / 2]);
+  const double threshold = med * factor;
+  int n = 0;
+  for (int c = 0; c < cells; c++) {
+    x_new[n++] = x[c];
+    if (err[c] >= threshold) x_new[n++] = 0.5 * (x[c] + x[c + 1]);
+  }
+  x_new[n++] = x[N - 1];
+  *N_new = n;
+  return scftb_spline(x + 1, eta_mid, x_new + 1, eta_mid_new, N - 2, n - 2, 1, 0.0);
 }
 
 // "N= %d, ERROR= %e" / "mean_field_free_energy, %2.15f" / rows "i,x,eta" (scft.cc:328-335)

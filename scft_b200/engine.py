@@ -46,7 +46,7 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_bind_global", "scftb_callback_nr1", "scftb_callback_c0", "scftb_callback_fixedpoint_c0",
            "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_broydn_device", "scftb_adm_chen_batch",
            "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
-           "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_write_solution",
+           "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_refine_mesh_adaptive", "scftb_write_solution",
            "scftb_read_solution", "scftb_read_res", "scftb2d_nccl_unique_id", "scftb2d_create", "scftb2d_destroy",
            "scftb2d_rows", "scftb2d_p2p_handle", "scftb2d_p2p_attach", "scftb2d_p2p_detach", "scftb2d_residual", "scftb2d_get_phi", "scftb2d_get_stats", "scftb2d_export_csr"]
 
@@ -92,6 +92,7 @@ def lib():
         L.scftb_get_march_ms.argtypes = [C.c_void_p, _dp, _ip]
         L.scftb_spline.argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double]
         L.scftb_refine_mesh.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
+        L.scftb_refine_mesh_adaptive.argtypes = [C.c_int, _dp, _dp, C.c_double, _ip, _dp, _dp]
         L.scftb_write_solution.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_double, _dp, _dp]
         L.scftb_read_solution.argtypes = [C.c_char_p, _ip, _dp, _dp, C.c_int]
         L.scftb_read_res.argtypes = [C.c_char_p, C.c_int, _dp, _dp, _dp]
@@ -279,6 +280,16 @@ def refine_mesh(x, eta_mid):
     xn, en = np.zeros(2 * N - 1), np.zeros(2 * N - 3)
     _chk(lib().scftb_refine_mesh(N, _p(x), _p(eta_mid), _p(xn), _p(en)))
     return xn, en
+
+
+def refine_mesh_adaptive(x, eta_mid, factor=10.0):
+    """scftb_refine_mesh_adaptive (Matlab_files/refine_mesh.m): (x_new, eta_mid_new) on a locally bisected mesh"""
+    x, eta_mid = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(eta_mid, dtype=np.float64)
+    N = len(x)
+    xn, en = np.zeros(2 * N - 1), np.zeros(2 * N - 3)
+    nn = C.c_int(0)
+    _chk(lib().scftb_refine_mesh_adaptive(N, _p(x), _p(eta_mid), factor, C.byref(nn), _p(xn), _p(en)))
+    return xn[: nn.value].copy(), en[: nn.value - 2].copy()
 
 
 def write_solution(path, err, F, x, eta_full):

@@ -82,3 +82,32 @@ def test_res_reader(sb, fixtures, tmp_path):
             fh.write(f" {a:.6e}  {b:.14e}  {c:.14e}  0.0  0.0\n")
     xl, phi, eta = sb.read_res(p, 33)
     assert np.allclose(eta, fixtures["res32_eta"], rtol=1e-14, atol=0) and np.allclose(phi, fixtures["res32_phi"], rtol=1e-14)
+
+
+def test_adaptive_refinement_follows_matlab_prototype(sb, oracle, fixtures):
+    """Matlab_files/refine_mesh.m: cells with |d eta/dx| >= 10 x median and the two wall cells are bisected.
+    The prototype's own mesh sequence 33 -> 43 -> 59 (Matlab_files/inputFiles/solution_yita_1D_N= 43/59.txt) is the
+    result of exactly this rule applied to its converged fields; the node COUNT after one refinement of the
+    N=33 deal.II field must be in that range and the new nodes must be midpoints of flagged cells."""
+    x = oracle.mesh_uniform(33)
+    em = fixtures["n33_eta"][1:-1]
+    xn, en = sb.refine_mesh_adaptive(x, em)
+    assert 35 <= len(xn) <= 65 and len(en) == len(xn) - 2
+    assert np.all(np.diff(xn) > 0) and xn[0] == x[0] and xn[-1] == x[-1]
+    assert set(np.round(x, 12)).issubset(set(np.round(xn, 12)))            # old nodes are kept
+    new = np.array(sorted(set(np.round(xn, 12)) - set(np.round(x, 12))))
+    mids = 0.5 * (x[:-1] + x[1:])
+    assert all(np.abs(mids - v).min() < 1e-12 for v in new)               # new nodes are cell midpoints
+    assert abs(new[0] - mids[0]) < 1e-12 and abs(new[-1] - mids[-1]) < 1e-12   # wall cells always cut
+    # flagged cells have the steepest field
+    grad = np.abs(np.diff(em) / np.diff(x[1:-1]))
+    thr = 10 * np.median(np.r_[np.inf, grad, np.inf])
+    expect = [mids[0]] + [mids[c + 1] for c in range(len(grad)) if grad[c] >= thr] + [mids[-1]]
+    assert np.allclose(new, expect, rtol=0, atol=1e-12)
+    ref = oracle.spline(x[1:-1], em, xn[1:-1], oracle.SPLINE_NOTAKNOT)
+    assert np.abs(en - ref).max() < 1e-11
+    # the MATLAB-era adaptive meshes in the reference's fixtures have the same structure: refined near the walls
+    for n_nodes in (43, 59):
+        xm = fixtures[f"matlab{n_nodes}_x"]
+        h = np.diff(xm)
+        assert h[:3].max() < h[len(h) // 2]
