@@ -149,27 +149,32 @@ int choose_kernel(int ni, bool uni, KernelChoice &kc) {
 }
 
 // IRK4 (complex solve): fewer nodes per thread, twice the coefficient storage
-int choose_kernel_irk4(int ni, KernelChoice &kc) {
+template <int C, int T>
+static march_fn pick4(bool uni) {
+  return uni ? (march_fn)march_irk4_kernel<C, T, true> : (march_fn)march_irk4_kernel<C, T, false>;
+}
+
+int choose_kernel_irk4(int ni, bool uni, KernelChoice &kc) {
   int C = 1;
   while (C < 8 && (ni + C - 1) / C > 256) C *= 2;
   int need = (ni + C - 1) / C;
   if (need > 256) return 1;
   int T = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 256));
   kc.fn = nullptr;
-  if (C == 1 && T == 32) kc.fn = (march_fn)march_irk4_kernel<1, 32>;
-  if (C == 1 && T == 64) kc.fn = (march_fn)march_irk4_kernel<1, 64>;
-  if (C == 1 && T == 128) kc.fn = (march_fn)march_irk4_kernel<1, 128>;
-  if (C == 1 && T == 256) kc.fn = (march_fn)march_irk4_kernel<1, 256>;
-  if (C == 2 && T == 256) kc.fn = (march_fn)march_irk4_kernel<2, 256>;
-  if (C == 4 && T == 256) kc.fn = (march_fn)march_irk4_kernel<4, 256>;
-  if (C == 8 && T == 256) kc.fn = (march_fn)march_irk4_kernel<8, 256>;
+  if (C == 1 && T == 32) kc.fn = pick4<1, 32>(uni);
+  if (C == 1 && T == 64) kc.fn = pick4<1, 64>(uni);
+  if (C == 1 && T == 128) kc.fn = pick4<1, 128>(uni);
+  if (C == 1 && T == 256) kc.fn = pick4<1, 256>(uni);
+  if (C == 2 && T == 256) kc.fn = pick4<2, 256>(uni);
+  if (C == 4 && T == 256) kc.fn = pick4<4, 256>(uni);
+  if (C == 8 && T == 256) kc.fn = pick4<8, 256>(uni);
   if (!kc.fn) return 1;
   kc.C = C; kc.T = T;
   return 0;
 }
 
 static int choose_any(int scheme, int ni, bool uni, KernelChoice &kc) {
-  return scheme == SCFTB_IRK4_CONSISTENT ? choose_kernel_irk4(ni, kc) : choose_kernel(ni, uni, kc);
+  return scheme == SCFTB_IRK4_CONSISTENT ? choose_kernel_irk4(ni, uni, kc) : choose_kernel(ni, uni, kc);
 }
 
 }  // namespace scftb

@@ -37,16 +37,16 @@ __device__ __forceinline__ cx rfma(cx a, double x, cx c) { return mk(fma(a.re, x
 __device__ __forceinline__ cx shfl_up_c(cx v, int d) { return mk(shfl_up_d(v.re, d), shfl_up_d(v.im, d)); }
 __device__ __forceinline__ cx shfl_dn_c(cx v, int d) { return mk(shfl_dn_d(v.re, d), shfl_dn_d(v.im, d)); }
 
-constexpr int PUBC = 10;  // doubles per warp: qf, zf(2), Z0(2), Z30(2), rsep(2)
+constexpr int PUBC = 12;  // doubles per warp: [0] qf, [2,3] zf, [4,5] Z0 (lane 0); [6,7] Z30 (lane 30); [8,9] rsep (lane 31)
 
-template <int C, int T>
+template <int C, int T, bool UNI>
 __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
   constexpr int CI = C - 1, CA = CI > 0 ? CI : 1, NW = T / 32, SL = T * C;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   __shared__ cx s_ex[2][T];
   __shared__ cx s_l3[NW][9];       // P, D, Nx, GL0, GR0, GL30, GR30, cAu(real), csu
   __shared__ cx s_minv[NW][NW];
-  __shared__ double s_pub[2][NW][PUBC];
+  __shared__ __align__(16) double s_pub[2][NW][PUBC];
   __shared__ double s_red[NW];
   const int n = P.nsteps;
   const double dt = 1.0 / n;
@@ -68,11 +68,13 @@ __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
     {
       Row rs = assemble_row(P, p, t * C + CI, L, dt);
       sAl = rs.Al; sAd = rs.Ad; sAu = rs.Au;
+      if (UNI) sAd = (rs.Al != 0.0) ? rs.Al : rs.Au;   // UNI: A's row is A_off (1,4,1); one coefficient is kept (march1d.cuh)
       if (t * C + CI >= P.ni) { sl = mk(0.0); sd = mk(1.0); su = mk(0.0); }   // padding: identity row
       else wrow(rs, sl, sd, su);
     }
     if constexpr (CI > 0) {
       cx Tl0 = mk(0.0), TuL = mk(0.0), pinv_prev = mk(0.0), Wu_prev = mk(0.0);
+      cx alo[CA];   // pinv_k * Wl_k (setup only)
 #pragma unroll
       for (int k = 0; k < CI; k++) {
         Row r = assemble_row(P, p, t * C + k, L, dt);
@@ -81,8 +83,10 @@ __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
         else wrow(r, wl, wd, wu);
         cx piv = (k == 0) ? wd : wd - (wl * pinv_prev) * Wu_prev;
         cx pinv = cinv(piv);
-        ca[k] = pinv * r.Al; cd[k] = pinv * r.Ad; cu[k] = pinv * r.Au;
-        al[k] = (k == 0) ? mk(0.0) : pinv * wl;
+        ca[k] = pinv * ((UNI && r.Al == 0.0) ? r.Au : r.Al); cd[k] = pinv * r.Ad; cu[k] = pinv * r.Au;
+        alo[k] = (k == 0) ? mk(0.0) : pinv * wl;
+        // UNI: the forward sweep runs on u = y / A_off (real right-hand side) with the plain multiplier Wl_k / piv_{k-1}
+        al[k] = (k == 0) ? mk(0.0) : (UNI ? wl * pinv_prev : alo[k]);
         be[k] = (k == CI - 1) ? mk(0.0) : pinv * wu;
         if (k == 0) Tl0 = pinv * wl;
         if (k == CI - 1) TuL = pinv * wu;
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
       cx y[CA];
       y[0] = Tl0;
 #pragma unroll
-      for (int k = 1; k < CI; k++) y[k] = -(al[k] * y[k - 1]);
+      for (int k = 1; k < CI; k++) y[k] = -(alo[k] * y[k - 1]);
       gl[CI - 1] = y[CI - 1];
 #pragma unroll
       for (int k = CI - 2; k >= 0; k--) gl[k] = nfma(be[k], gl[k + 1], y[k]);
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
     const cx GL = pcr(A0), GR = pcr(C30);
     // ---------------------------------------------------------------- level 3 setup
     if (lane == 31) { s_l3[wid][0] = l3P; s_l3[wid][1] = l3D; s_l3[wid][2] = l3N;
-                      s_l3[wid][7] = mk(sAu); s_l3[wid][8] = (CI > 0) ? su : mk(0.0); }
+                      s_l3[wid][7] = mk((wid + 1 < NW) ? (UNI ? sAd : sAu) : 0.0); s_l3[wid][8] = (CI > 0) ? su : mk(0.0); }
     if (lane == 0) { s_l3[wid][3] = GL; s_l3[wid][4] = GR; }
     if (lane == 30) { s_l3[wid][5] = GL; s_l3[wid][6] = GR; }
     __syncthreads();
@@ -170,6 +174,11 @@ __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
     }
     __syncthreads();
 
+    // the lane's share of the level-3 solve (march1d.cuh): lane v3 forms R_v3, butterfly sum over NW lanes
+    const int v3 = lane & (NW - 1);
+    const cx c3P = s_l3[v3][0], c3su = s_l3[v3][8], c3Nx = s_l3[v3][2];
+    const double c3Au = s_l3[v3][7].re;
+    const cx mW = s_minv[wid][v3], mM = (wid > 0) ? s_minv[(wid + NW - 1) % NW][v3] : mk(0.0);
     // ---------------------------------------------------------------- initial condition
     double q[C], phi[C];
 #pragma unroll
@@ -191,26 +200,38 @@ __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
 #pragma unroll
         for (int k = 0; k < C; k++) qo[k] = hs[hidx(k)];
       }
-      // rhs A q (real), scaled by the complex pivots; chunk solve with zero separators
+      // rhs A q (real); chunk solve with zero separators
       cx z[CA];
       cx zlast = mk(0.0), z0 = mk(0.0);
       if constexpr (CI > 0) {
+        if constexpr (UNI) {
 #pragma unroll
-        for (int k = 0; k < CI; k++) {
-          double qm = (k == 0) ? XL : q[k - 1], qp = q[k + 1];
-          cx bk = rfma(ca[k], qm, rfma(cu[k], qp, cd[k] * q[k]));
-          z[k] = (k == 0) ? bk : nfma(al[k], z[k - 1], bk);
+          for (int k = 0; k < CI; k++) {
+            double qm = (k == 0) ? XL : q[k - 1], qp = q[k + 1];
+            const double tk = fma(4.0, q[k], qm + qp);
+            z[k] = (k == 0) ? mk(tk) : nfma(al[k], z[k - 1], mk(tk));
+          }
+          z[CI - 1] = ca[CI - 1] * z[CI - 1];
+#pragma unroll
+          for (int k = CI - 2; k >= 0; k--) z[k] = nfma(be[k], z[k + 1], ca[k] * z[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < CI; k++) {
+            double qm = (k == 0) ? XL : q[k - 1], qp = q[k + 1];
+            cx bk = rfma(ca[k], qm, rfma(cu[k], qp, cd[k] * q[k]));
+            z[k] = (k == 0) ? bk : nfma(al[k], z[k - 1], bk);
+          }
+#pragma unroll
+          for (int k = CI - 2; k >= 0; k--) z[k] = nfma(be[k], z[k + 1], z[k]);
         }
-#pragma unroll
-        for (int k = CI - 2; k >= 0; k--) z[k] = nfma(be[k], z[k + 1], z[k]);
         zlast = z[CI - 1]; z0 = z[0];
       }
       const double qprev = (CI > 0) ? q[CI > 0 ? CI - 1 : 0] : XL;
-      cx r = mk(fma(sAl, qprev, sAd * q[C - 1]));
+      cx r = mk(UNI ? sAd * fma(4.0, q[C - 1], qprev) : fma(sAl, qprev, sAd * q[C - 1]));
       if constexpr (CI > 0) r = nfma(sl, zlast, r);
       const cx rsep = r;
       {
-        r.re = fma(sAu, qn, r.re);
+        r.re = fma(UNI ? sAd : sAu, qn, r.re);
         if constexpr (CI > 0) { cx zfn = shfl_dn_c(z0, 1); r = nfma(su, zfn, r); }
       }
       if (lane == 31) r = mk(0.0);
@@ -222,23 +243,23 @@ __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
       }
       const cx Z = r * binv;
       double *pb = s_pub[j & 1][wid];
-      if (lane == 0) { pb[0] = q[0]; pb[1] = z0.re; pb[2] = z0.im; pb[3] = Z.re; pb[4] = Z.im; }
-      if (lane == 30) { pb[5] = Z.re; pb[6] = Z.im; }
-      if (lane == 31) { pb[7] = rsep.re; pb[8] = rsep.im; }
+      if (lane == 0) { pb[0] = q[0]; pb[2] = z0.re; pb[3] = z0.im; pb[4] = Z.re; pb[5] = Z.im; }
+      if (lane == 30) { pb[6] = Z.re; pb[7] = Z.im; }
+      if (lane == 31) { pb[8] = rsep.re; pb[9] = rsep.im; }
       if constexpr (NW > 1) __syncthreads(); else __syncwarp();
-      cx Wm = mk(0.0), Ww = mk(0.0);
+      cx Wm, Ww;
+      {
+        const double *pv = s_pub[j & 1][v3], *pn = s_pub[j & 1][(v3 + 1) % NW];
+        cx R = nfma(c3P, mk(pv[6], pv[7]), mk(pv[8], pv[9]));
+        cx R2 = nfma(c3su, mk(pn[2], pn[3]), mk(c3Au * pn[0]));
+        R2 = nfma(c3Nx, mk(pn[4], pn[5]), R2);
+        R = R + R2;
+        Ww = mW * R; Wm = mM * R;
 #pragma unroll
-      for (int v = 0; v < NW; v++) {
-        const double *pv = s_pub[j & 1][v];
-        cx R = nfma(s_l3[v][0], mk(pv[5], pv[6]), mk(pv[7], pv[8]));
-        if (v + 1 < NW) {
-          const double *pn = s_pub[j & 1][(v + 1) % NW];
-          R.re = fma(s_l3[v][7].re, pn[0], R.re);
-          R = nfma(s_l3[v][8], mk(pn[1], pn[2]), R);
-          R = nfma(s_l3[v][2], mk(pn[3], pn[4]), R);
+        for (int d = 1; d < NW; d <<= 1) {
+          Ww.re += __shfl_xor_sync(0xffffffffu, Ww.re, d); Ww.im += __shfl_xor_sync(0xffffffffu, Ww.im, d);
+          Wm.re += __shfl_xor_sync(0xffffffffu, Wm.re, d); Wm.im += __shfl_xor_sync(0xffffffffu, Wm.im, d);
         }
-        Ww = pfma(s_minv[wid][v], R, Ww);
-        if (NW > 1 && wid > 0) Wm = pfma(s_minv[(wid + NW - 1) % NW][v], R, Wm);
       }
       const cx Y = (lane == 31) ? Ww : nfma(GL, Wm, nfma(GR, Ww, Z));   // solution at the own separator
       cx YL = shfl_up_c(Y, 1);
