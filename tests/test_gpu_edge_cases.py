@@ -82,3 +82,17 @@ def test_mixer_window_limits(sb):
     done, iters, err = m.status(0)
     assert err[0] > 0
     m.close(); eng.close()
+
+
+def test_odd_number_of_steps_with_trapezoid(sb, oracle, fixtures):
+    """no unpaired middle slice when n is odd: every slice j > n/2 pairs with n-j < n/2"""
+    N = 33
+    x = oracle.mesh_uniform(N)
+    em = fixtures["res32_eta"][1:-1]
+    for n in (33, 7, 3):
+        for scheme in (0, 2):
+            eng = sb.Engine(N, nsteps=n, scheme=scheme, quadrature=sb.QUAD_TRAPEZOID)
+            eng.residual(em)
+            ref = oracle.residual(oracle.eta_full(x, em), oracle.f0_given(x), scheme=scheme, nsteps=n, quadrature=1)
+            assert np.abs(eng.phi() - ref["phi"]).max() < 1e-10 * np.abs(ref["phi"]).max()
+            eng.close()
