@@ -363,15 +363,15 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
           for (int k = 0; k < C; k += 2) cp_async16(dst + (k / 2) * T * 16, src + k * T);
         }
       }
-      if (STAGE) cp_async_commit();
     };
-    prefetch(1, hr - SL);
 
     // ------------------------------------------------------------------ the contour march
     for (int j = 1; j <= n; j++) {
       hw += SL; hr -= SL;
       const bool pairing = (2 * j > n);
-      prefetch(j + 1, hr - SL);   // the slice the NEXT step pairs with; written >= 1 step ago by this thread
+      // the slice the NEXT step pairs with is fetched a whole step ahead when it was stored in an earlier step
+      // (2j >= n); for odd n the very first pairing uses the slice of THIS step and is fetched after its store
+      if (2 * j >= n) prefetch(j + 1, hr - SL);
       // right-hand side b = A q and the level-1 (chunk) solve with zero separators, UL order
       double z[CA];
       double zlast = 0.0, z0 = 0.0, zfn = 0.0;
@@ -460,6 +460,8 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
       qn = (lane == 31) ? 0.0 : qn;   // supplied through the publish buffer
       // history + fused quadrature
       if (full || 2 * j < n) store_slice(hw);
+      if (2 * j < n && 2 * (j + 1) > n) prefetch(j + 1, hr - SL);   // odd n: slice (n-1)/2, written just above
+      if (STAGE) cp_async_commit();                                  // exactly one group per step
       if (2 * j >= n) {
         const double wj = __ldg(wq + j);   // j > n/2: 2*w_j (pair j, n-j); j == n/2: w_j
         if (pairing) {

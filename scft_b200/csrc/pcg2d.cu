@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -211,6 +212,13 @@ __device__ __forceinline__ double gather(const double *v, int c, const Sys2D &S)
 template <bool PEER = false>
 __device__ Part cg_spmv(const Sys2D &S, const Vec2D &V, int tid, int nthreads, int phase = 0) {
   Part acc = {0, 0, 0, 0};
+  // no aliasing between the matrix, the gathered vector and the output: lets the loads of the next rows issue early
+  const double *__restrict__ valT = S.valT;
+  const int *__restrict__ col = S.col;
+  const double *__restrict__ zv = V.z;
+  const double *__restrict__ rv = V.r;
+  double *__restrict__ sv_out = V.s;
+#pragma unroll 2
   for (int i = tid; i < S.nslices * 32; i += nthreads) {
     if (i >= S.nrows) continue;
     if (phase != 0) {   // rows of the first / last owned node column are the only ones that read halo entries
@@ -219,9 +227,9 @@ __device__ Part cg_spmv(const Sys2D &S, const Vec2D &V, int tid, int nthreads, i
     }
     double sv = 0.0;
 #pragma unroll
-    for (int k = 0; k < SLOTS; k++) sv = fma(S.valT[sell(i, k)], gather<PEER>(V.z, S.col[sell(i, k)], S), sv);
-    V.s[i] = sv;
-    const double r = V.r[i], z = V.z[i];
+    for (int k = 0; k < SLOTS; k++) sv = fma(valT[sell(i, k)], gather<PEER>(zv, col[sell(i, k)], S), sv);
+    sv_out[i] = sv;
+    const double r = rv[i], z = zv[i];
     acc.a = fma(r, z, acc.a); acc.b = fma(z, sv, acc.b); acc.c = fma(r, r, acc.c);
   }
   return acc;
@@ -229,12 +237,15 @@ __device__ Part cg_spmv(const Sys2D &S, const Vec2D &V, int tid, int nthreads, i
 
 // p = z + beta p; w = s + beta w; x += alpha p; r -= alpha w; z = D^-1 r
 __device__ void cg_update(const Sys2D &S, const Vec2D &V, double alpha, double beta, int tid, int nthreads) {
+  double *__restrict__ pv = V.p, *__restrict__ wv = V.w, *__restrict__ xv = V.x, *__restrict__ rv = V.r, *__restrict__ zv = V.z;
+  const double *__restrict__ sv = V.s, *__restrict__ dinv = S.dinv;
+#pragma unroll 4
   for (int i = tid; i < S.nrows; i += nthreads) {
-    const double p = fma(beta, V.p[i], V.z[i]), w = fma(beta, V.w[i], V.s[i]);
-    V.p[i] = p; V.w[i] = w;
-    V.x[i] = fma(alpha, p, V.x[i]);
-    const double r = fma(-alpha, w, V.r[i]);
-    V.r[i] = r; V.z[i] = S.dinv[i] * r;
+    const double p = fma(beta, pv[i], zv[i]), w = fma(beta, wv[i], sv[i]);
+    pv[i] = p; wv[i] = w;
+    xv[i] = fma(alpha, p, xv[i]);
+    const double r = fma(-alpha, w, rv[i]);
+    rv[i] = r; zv[i] = dinv[i] * r;
   }
 }
 
@@ -266,7 +277,7 @@ __device__ void step_end(const March2D &M, int j, int tid, int nthreads) {
 
 // ------------------------------------------------------------------------------------------------
 // single GPU: the whole march in one persistent cooperative kernel
-__global__ void __launch_bounds__(TPB2) march2d_persistent_kernel(March2D M) {
+__global__ void __launch_bounds__(TPB2, 5) march2d_persistent_kernel(March2D M) {
   cg::grid_group grid = cg::this_grid();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const Sys2D &S = M.S; const Vec2D &V = M.V;
@@ -414,7 +425,7 @@ __device__ Part allreduce_partials(const P2P &X, const double *partial, int nblo
   return t;
 }
 
-__global__ void __launch_bounds__(TPB2) march2d_p2p_kernel(March2D M, P2P X, ull seq0, ull rseq0) {
+__global__ void __launch_bounds__(TPB2, 5) march2d_p2p_kernel(March2D M, P2P X, ull seq0, ull rseq0) {
   cg::grid_group grid = cg::this_grid();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const Sys2D &S = M.S; const Vec2D &V = M.V;
@@ -745,7 +756,10 @@ int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_en
     CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, march2d_p2p_kernel, TPB2, 0));
     if (cfg->world > 1) occ = std::min(occ, occp);
   }
-  occ = std::max(1, std::min(occ, 4));
+  {
+    const char *cap = getenv("SCFTB_2D_BLOCKS_PER_SM");   // tuning knob; default 8 (memory-latency bound: more warps in flight)
+    occ = std::max(1, std::min(occ, cap ? atoi(cap) : 8));
+  }
   e->grid_persist = std::max(1, std::min(sms * occ, (e->nrows + 4 * TPB2 - 1) / (4 * TPB2)));   // small meshes: fewer blocks, cheaper barriers
   int occ2 = 0;
   CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, spmv_kernel, TPB2, 0));
