@@ -1,3 +1,4 @@
-python -m pytest tests/test_gpu_edge_cases.py tests/test_gpu_pcg2d.py -m gpu -q 2>&1 | tail -2
-for b in 4 8; do SCFTB_2D_BLOCKS_PER_SM=$b python tools/bench2d.py 1023 1023 16 2>&1 | tail -1 | cut -c1-220; done
-SCFTB_2D_BLOCKS_PER_SM=8 python tools/bench2d.py 1023 1023 2048 2>&1 | tail -1 | cut -c1-220
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q 2>&1 | tail -2
+python tools/lat.py 0 2>&1 | tail -5
+python bench.py > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err; cut -c1-200 gpurun_out/bench_r1_final.json

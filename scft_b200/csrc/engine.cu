@@ -119,13 +119,14 @@ __global__ void spline_bnd_kernel(int nprob, int N, const double *x, const doubl
 
 // ---------------------------------------------------------------------------------------------
 template <int C, int T, int MINB>
-static march_fn pick(bool uni) {
-  return uni ? (march_fn)march_ie_kernel<C, T, true, MINB> : (march_fn)march_ie_kernel<C, T, false, MINB>;
+static march_fn pick(bool uni, bool odd) {
+  if (odd) return uni ? (march_fn)march_ie_kernel<C, T, true, MINB, true> : (march_fn)march_ie_kernel<C, T, false, MINB, true>;
+  return uni ? (march_fn)march_ie_kernel<C, T, true, MINB, false> : (march_fn)march_ie_kernel<C, T, false, MINB, false>;
 }
 
 // nodes per thread C and threads per problem T for ni interior nodes.  SCFTB_FORCE_C=4 selects the
 // 256-thread / 4-nodes-per-thread variant where it applies (tuning experiments).
-int choose_kernel(int ni, bool uni, KernelChoice &kc) {
+int choose_kernel(int ni, bool uni, KernelChoice &kc, bool odd) {
   int C = 1;
   while (C < 16 && (ni + C - 1) / C > 128) C *= 2;
   const char *force = getenv("SCFTB_FORCE_C");
@@ -134,15 +135,15 @@ int choose_kernel(int ni, bool uni, KernelChoice &kc) {
   int T = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 256));
   if (need > 256) return 1;
   kc.fn = nullptr;
-  if (C == 1 && T == 32) kc.fn = pick<1, 32, 8>(uni);
-  if (C == 1 && T == 64) kc.fn = pick<1, 64, 6>(uni);
-  if (C == 1 && T == 128) kc.fn = pick<1, 128, 4>(uni);
-  if (C == 2 && T == 128) kc.fn = pick<2, 128, 4>(uni);
-  if (C == 4 && T == 128) kc.fn = pick<4, 128, 4>(uni);
-  if (C == 4 && T == 256) kc.fn = pick<4, 256, 2>(uni);
-  if (C == 8 && T == 128) kc.fn = pick<8, 128, 3>(uni);
-  if (C == 16 && T == 128) kc.fn = pick<16, 128, 1>(uni);
-  if (C == 16 && T == 256) kc.fn = pick<16, 256, 1>(uni);
+  if (C == 1 && T == 32) kc.fn = pick<1, 32, 8>(uni, odd);
+  if (C == 1 && T == 64) kc.fn = pick<1, 64, 6>(uni, odd);
+  if (C == 1 && T == 128) kc.fn = pick<1, 128, 4>(uni, odd);
+  if (C == 2 && T == 128) kc.fn = pick<2, 128, 4>(uni, odd);
+  if (C == 4 && T == 128) kc.fn = pick<4, 128, 4>(uni, odd);
+  if (C == 4 && T == 256) kc.fn = pick<4, 256, 2>(uni, odd);
+  if (C == 8 && T == 128) kc.fn = pick<8, 128, 3>(uni, odd);
+  if (C == 16 && T == 128) kc.fn = pick<16, 128, 1>(uni, odd);
+  if (C == 16 && T == 256) kc.fn = pick<16, 256, 1>(uni, odd);
   if (!kc.fn) return 1;
   kc.C = C; kc.T = T;
   return 0;
@@ -173,8 +174,8 @@ int choose_kernel_irk4(int ni, bool uni, KernelChoice &kc) {
   return 0;
 }
 
-static int choose_any(int scheme, int ni, bool uni, KernelChoice &kc) {
-  return scheme == SCFTB_IRK4_CONSISTENT ? choose_kernel_irk4(ni, uni, kc) : choose_kernel(ni, uni, kc);
+static int choose_any(int scheme, int ni, bool uni, KernelChoice &kc, int nsteps) {
+  return scheme == SCFTB_IRK4_CONSISTENT ? choose_kernel_irk4(ni, uni, kc) : choose_kernel(ni, uni, kc, (nsteps & 1) != 0);
 }
 
 }  // namespace scftb
@@ -235,7 +236,7 @@ int scftb_create(const scftb_config *cfg, scftb_engine **out) {
   // sum_j w_j q_j q_{n-j} = sum_{j>n/2} 2 w_j q_j q_{n-j} + [n even] w_{n/2} q_{n/2}^2
   std::vector<double> wq(e->h_w);
   for (int j = 0; j <= n; j++) wq[j] = (2 * j > n) ? 2.0 * e->h_w[j] : ((2 * j == n) ? e->h_w[j] : 0.0);
-  if (choose_any(cfg->scheme, e->ni, true, e->kc)) {
+  if (choose_any(cfg->scheme, e->ni, true, e->kc, cfg->nsteps)) {
     delete e;
     return fail(SCFTB_ERR_ARG, "N too large for the register-resident march (N <= 4098 in this build)");
   }
@@ -320,7 +321,7 @@ int scftb_set_problem(scftb_engine *e, int p, double tau, double L, const double
     for (int q = 0; q < B; q++)
       for (int i = 0; i < N; i++) e->h_x[(size_t)q * N + i] = e->h_L[q] * i / (N - 1);
     e->uniform = false;
-    if (choose_any(e->cfg.scheme, e->ni, false, e->kc)) return fail(SCFTB_ERR_ARG, "N too large");
+    if (choose_any(e->cfg.scheme, e->ni, false, e->kc, e->cfg.nsteps)) return fail(SCFTB_ERR_ARG, "N too large");
   }
   std::vector<double> xs(N);
   for (int q = (p < 0 ? 0 : p); q < (p < 0 ? B : p + 1); q++) {

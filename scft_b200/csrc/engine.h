@@ -25,7 +25,7 @@ struct KernelChoice {
   march_fn fn;
 };
 extern std::atomic<long> g_launches;
-int choose_kernel(int ni, bool uni, KernelChoice &kc);
+int choose_kernel(int ni, bool uni, KernelChoice &kc, bool odd);
 }  // namespace scftb
 
 #define CK(call)                                                                                   \

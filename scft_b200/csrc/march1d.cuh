@@ -145,7 +145,9 @@ __host__ __device__ inline int hist_index(int C, int T, int t, int k) {
 
 constexpr int PUB = 8;  // doubles per warp in a publish buffer: [0] qf, [1] zf, [2] Z0 (lane 0); [4] Z30 (lane 30), [5] rsep (lane 31)
 
-template <int C, int T, bool UNI, int MINB>
+// ODDN: instantiation for an odd number of contour steps (only then the first pairing step needs its partner slice
+// re-read; keeping it out of the even-n instantiation leaves the hot loop's register allocation untouched)
+template <int C, int T, bool UNI, int MINB, bool ODDN>
 __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
   static_assert(C == 1 || (C % 2) == 0, "C must be 1 or even");
   constexpr int CI = C - 1;             // chunk-interior nodes per thread
@@ -363,15 +365,30 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
           for (int k = 0; k < C; k += 2) cp_async16(dst + (k / 2) * T * 16, src + k * T);
         }
       }
+      if (STAGE) cp_async_commit();
     };
+    prefetch(1, hr - SL);
 
     // ------------------------------------------------------------------ the contour march
     for (int j = 1; j <= n; j++) {
       hw += SL; hr -= SL;
       const bool pairing = (2 * j > n);
-      // the slice the NEXT step pairs with is fetched a whole step ahead when it was stored in an earlier step
-      // (2j >= n); for odd n the very first pairing uses the slice of THIS step and is fetched after its store
-      if (2 * j >= n) prefetch(j + 1, hr - SL);
+      // the slice the NEXT step pairs with is fetched a whole step ahead.  For odd n the first pairing step
+      // (j = (n+1)/2) pairs with the slice stored one step earlier, which was not written yet when its prefetch
+      // was issued: once, copy it into the staging buffer with ordinary loads (ordered after this thread's store)
+      if (ODDN && STAGE && 2 * j == n + 1) {
+        cp_async_wait0();   // the stale prefetch into this buffer has landed and can be overwritten
+        const unsigned dst = qo_me + (j & 1) * QO_BUF;
+        if constexpr (C == 1) sts64(dst, hr[0]);
+        else {
+#pragma unroll
+          for (int k = 0; k < C; k += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(hr + k * T);
+            sts128(dst + (k / 2) * T * 16, v.x, v.y);
+          }
+        }
+      }
+      prefetch(j + 1, hr - SL);
       // right-hand side b = A q and the level-1 (chunk) solve with zero separators, UL order
       double z[CA];
       double zlast = 0.0, z0 = 0.0, zfn = 0.0;
@@ -460,8 +477,6 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
       qn = (lane == 31) ? 0.0 : qn;   // supplied through the publish buffer
       // history + fused quadrature
       if (full || 2 * j < n) store_slice(hw);
-      if (2 * j < n && 2 * (j + 1) > n) prefetch(j + 1, hr - SL);   // odd n: slice (n-1)/2, written just above
-      if (STAGE) cp_async_commit();                                  // exactly one group per step
       if (2 * j >= n) {
         const double wj = __ldg(wq + j);   // j > n/2: 2*w_j (pair j, n-j); j == n/2: w_j
         if (pairing) {
