@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q 2>&1 | tail -2
-python tools/lat.py 0 2>&1 | tail -5
-python bench.py > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err; cut -c1-200 gpurun_out/bench_r1_final.json
+python -m pytest tests/test_gpu_broyden_device.py tests/test_gpu_sweep_converge.py -q 2>&1 | tail -15
+python tools/sweep_converge.py 32 2>&1 | tail -15 | tee gpurun_out/sweep_converge_1gpu.txt

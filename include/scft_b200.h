@@ -121,6 +121,13 @@ int scftb_broydn(scftb_func f, double *x, int n, int *check, double *err, int *j
  * few scalars per step.  Solves problem 0 of the engine, whose first N-2 problems must share its (tau, L, mesh)
  * (scftb_set_problem(e, -1, ...)); x[N-2] host in/out; check / err / jc as scftb_broydn. */
 int scftb_broydn_device(scftb_engine *e, double *x, int *check, double *err, int *jc);
+/* Same with options.  SCFTB_BROYDN_KEEP_TRIAL: when the line search stops on its step-size test
+ * (lnsrch.c: alam < alamin) the reference resets x to the previous iterate but reports the residual norm of
+ * the trial point, so a "converged" return can carry a field whose own residual is above the tolerance
+ * (broydn.c:215-228).  With this flag a trial point that meets the tolerance is returned itself, so that
+ * *err is the residual norm of the returned x. */
+#define SCFTB_BROYDN_KEEP_TRIAL 1
+int scftb_broydn_device_ex(scftb_engine *e, double *x, int *check, double *err, int *jc, int flags);
 
 /* Device-resident batched Anderson mixing (adm_chen semantics) on the engine's problems:
  * x[nprob][N-2] host in/out.  All nprob problems iterate in lock-step, each with its own

@@ -116,12 +116,15 @@ __global__ void __launch_bounds__(32) qrdcmp_kernel(int n, double *a, double *c,
         const double tau = sum / ck;
         for (int i = k; i < n; i++) a[(size_t)i * n + j] = fma(-tau, vk[i - k], a[(size_t)i * n + j]);
       }
-      if (k / 32 == blockIdx.x) {   // the owner of column k stores the reflector and the scalars
-        for (int i = k + lane; i < n; i += 32) a[(size_t)i * n + k] = vk[i - k];
-        if (lane == 0) { c[k] = ck; d[k] = -sc * sigma; }
-      }
+      if (k / 32 == blockIdx.x && lane == 0) { c[k] = ck; d[k] = -sc * sigma; }
     }
+    // every warp reads column k at the top of this step, so its owner may overwrite it with the reflector only
+    // after the grid barrier (nobody touches column k any more in the later steps)
     grid.sync();
+    if (sc != 0.0 && k / 32 == blockIdx.x) {
+      for (int i = k + lane; i < n; i += 32) a[(size_t)i * n + k] = vk[i - k];
+      __syncwarp();
+    }
   }
   if (blockIdx.x == 0 && lane == 0) {
     d[n - 1] = a[(size_t)(n - 1) * n + n - 1];
@@ -316,7 +319,12 @@ struct BroydenDev {
 static BroydenDev g_bd;   // plays the role of the caller-owned globals qt, r, d (broydn.c:22-28): kept across calls for jc
 
 extern "C" int scftb_broydn_device(scftb_engine *e, double *x_host, int *check, double *err, int *jc) {
+  return scftb_broydn_device_ex(e, x_host, check, err, jc, 0);
+}
+
+extern "C" int scftb_broydn_device_ex(scftb_engine *e, double *x_host, int *check, double *err, int *jc, int flags) {
   if (!e || !x_host || !check || !err || !jc) return fail(SCFTB_ERR_ARG, "broydn_device: bad argument");
+  const bool keep_trial = (flags & SCFTB_BROYDN_KEEP_TRIAL) != 0;
   const int n = e->ni;
   const int MAXITS = 400;
   const double TOLX = 1e-14, STPMX = 100.0, TOLF = *err, TOLMIN = TOLF;
@@ -436,7 +444,10 @@ extern "C" int scftb_broydn_device(scftb_engine *e, double *x_host, int *check, 
       rc = eval(f, emax);
       if (rc == SCFTB_ERR_NAN) { f = INFINITY; emax = INFINITY; }   // a NaN trial behaves like a rejected step
       else if (rc) return rc;
-      if (alam < alamin) { CK(cudaMemcpyAsync(x, xold, 8 * (size_t)n, cudaMemcpyDeviceToDevice, st)); *check = 1; break; }
+      if (alam < alamin) {
+        if (keep_trial && emax < TOLF) break;   // the trial itself is a solution: return it, not the previous iterate
+        CK(cudaMemcpyAsync(x, xold, 8 * (size_t)n, cudaMemcpyDeviceToDevice, st)); *check = 1; break;
+      }
       else if (f <= fold + ALF * alam * slope) break;
       else {
         if (alam == 1.0) tmplam = -slope / (2.0 * (f - fold - slope));

@@ -44,7 +44,7 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_residual", "scftb_residual_batch", "scftb_residual_batch_device", "scftb_get_phi", "scftb_get_Q",
            "scftb_get_f0_given", "scftb_get_eta_full", "scftb_get_q_history", "scftb_free_energy",
            "scftb_bind_global", "scftb_callback_nr1", "scftb_callback_c0", "scftb_callback_fixedpoint_c0",
-           "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_broydn_device", "scftb_adm_chen_batch",
+           "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_broydn_device", "scftb_broydn_device_ex", "scftb_adm_chen_batch",
            "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
            "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_refine_mesh_adaptive", "scftb_write_solution",
            "scftb_read_solution", "scftb_read_res", "scftb2d_nccl_unique_id", "scftb2d_create", "scftb2d_destroy",
@@ -78,6 +78,7 @@ def lib():
         L.scftb_adm.argtypes = [C.c_void_p, _dp, C.c_int, _ip, C.c_int]
         L.scftb_broydn.argtypes = [C.c_void_p, _dp, C.c_int, _ip, _dp, _ip]
         L.scftb_broydn_device.argtypes = [C.c_void_p, _dp, _ip, _dp, _ip]
+        L.scftb_broydn_device_ex.argtypes = [C.c_void_p, _dp, _ip, _dp, _ip, C.c_int]
         L.scftb_adm_chen_batch.argtypes = [C.c_void_p, C.c_int, _dp, C.c_double, C.c_int, C.c_double, C.c_int,
                                            C.c_int, _ip, _dp]
         L.scftb_mixer_create.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
@@ -198,11 +199,11 @@ class Engine:
         _chk(lib().scftb_free_energy(self._h, p, f0bar, C.byref(F)))
         return F.value
 
-    def broydn_device(self, x0, tolf, jc=0):
-        """scftb_broydn_device: (rc, check, x, err, jc)"""
+    def broydn_device(self, x0, tolf, jc=0, keep_trial=False):
+        """scftb_broydn_device[_ex]: (rc, check, x, err, jc); keep_trial = SCFTB_BROYDN_KEEP_TRIAL"""
         x = np.ascontiguousarray(x0, dtype=np.float64).copy()
         chk, err, jcv = C.c_int(1), C.c_double(tolf), C.c_int(jc)
-        rc = lib().scftb_broydn_device(self._h, _p(x), C.byref(chk), C.byref(err), C.byref(jcv))
+        rc = lib().scftb_broydn_device_ex(self._h, _p(x), C.byref(chk), C.byref(err), C.byref(jcv), int(keep_trial))
         if rc not in (0, 4):
             _chk(rc)
         return rc, chk.value, x, err.value, jcv.value

@@ -88,7 +88,7 @@ int main(int argc, char **argv) {
     } else if (solver == "broydn_dev") {   // the same iteration with Jacobian, QR and updates resident on the device
       double err = tol;
       int jc = 0;
-      rc = scftb_broydn_device(e, xm.data(), &check, &err, &jc);
+      rc = scftb_broydn_device_ex(e, xm.data(), &check, &err, &jc, SCFTB_BROYDN_KEEP_TRIAL);
     } else {  // staged schedule of drivescft.cc:294-298
       const double st[5][4] = {{1e-1, 200, 0.99, 2}, {1e-3, 300, 0.9, 3}, {1e-7, 800, 0.9, 15}, {1e-7, 1000, 0.9, 30},
                                {1e-7, 10000, 0.1, 50}};

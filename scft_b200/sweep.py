@@ -64,3 +64,75 @@ def run_sharded(total, rank, world, evaluate):
     """evaluate(p0, p1) -> [p1-p0, k] results of this rank's block; returns the gathered [total, k]."""
     p0, p1 = shard(total, rank, world)
     return gather_results(evaluate(p0, p1), total, rank, world)
+
+
+# ------------------------------------------------------------------------------------------------
+# time-to-converge of sweep problems: the reference's continuation flow (drivescft.cc:259-322: solve on N=33,
+# refine every cell, transfer the field by spline, solve again ... up to the target mesh) with the device-resident
+# Broyden solver on every level.  One set of per-level engines is reused for all problems of a rank.
+class Continuation:
+    """levels N = 33, 65, ..., N_target on uniform meshes; scheme/nsteps as in Engine."""
+
+    def __init__(self, N_target=1025, N0=33, nsteps=2048, scheme=None, device=0, tol=1e-9, retries=2):
+        from . import engine as E
+        self.E = E
+        self.tol, self.retries = tol, retries
+        self.levels = []
+        N = N0
+        while True:
+            self.levels.append(N)
+            if N >= N_target:
+                break
+            N = 2 * N - 1
+        if self.levels[-1] != N_target:
+            raise ValueError(f"N_target={N_target} is not reachable from N0={N0} by bisection")
+        scheme = E.IE_ROWSCALE if scheme is None else scheme
+        self.engines = [E.Engine(N, nsteps=nsteps, scheme=scheme, max_batch=N - 2, device=device) for N in self.levels]
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+        self.engines = []
+
+    def solve(self, tau, L, eta_mid0):
+        """eta_mid0: interior field on the coarsest level.  Returns dict(check, err, eta_mid, F, Q, level_err)."""
+        E = self.E
+        eta = np.ascontiguousarray(eta_mid0, dtype=np.float64)
+        assert len(eta) == self.levels[0] - 2
+        level_err, check, err, attempts = [], 1, float("nan"), 0
+        for lvl, (N, eng) in enumerate(zip(self.levels, self.engines)):
+            eng.set_problem(-1, tau, L)
+            if lvl:
+                _, eta = E.refine_mesh(np.linspace(0.0, L, self.levels[lvl - 1]), eta)
+            for attempt in range(1 + self.retries):
+                # a line-search stall (check=1) just above the tolerance restarts from the returned field with a
+                # fresh Jacobian, which is what a user of broydn.c does by calling it again (1D_FEM.c:356)
+                _, check, eta, err, _ = eng.broydn_device(eta, self.tol, keep_trial=True)
+                attempts += 1
+                if check == 0 or not np.isfinite(err):
+                    break
+            level_err.append(err)
+            if check != 0:
+                break
+        eng = self.engines[len(level_err) - 1]
+        eng.residual(eta)  # phi, Q and the boundary values of the returned field for F
+        return dict(check=check, err=err, eta_mid=eta, F=eng.free_energy(0, f0bar=0.0), Q=eng.Q(0), level_err=level_err, attempts=attempts,
+                    N=self.levels[len(level_err) - 1])
+
+
+def converge_block(p0, p1, eta33_mid, N_target=1025, nsteps=2048, scheme=None, device=0, tol=1e-9):
+    """Converge sweep problems [p0, p1) (sweep_params; initial field eta33_mid * (1 + 0.05 z_p) on N=33).
+    Returns rows [check, err, F, Q, seconds]."""
+    import time
+    cont = Continuation(N_target, len(eta33_mid) + 2, nsteps, scheme, device, tol)
+    rows = np.zeros((p1 - p0, 5))
+    try:
+        for i, p in enumerate(range(p0, p1)):
+            tau, L, seed = sweep_params(p)
+            z = np.random.default_rng(seed).standard_normal(len(eta33_mid))
+            t0 = time.perf_counter()
+            r = cont.solve(tau, L, eta33_mid * (1 + 0.05 * z))
+            rows[i] = (r["check"], r["err"], r["F"], r["Q"], time.perf_counter() - t0)
+    finally:
+        cont.close()
+    return rows

@@ -61,3 +61,36 @@ def test_device_broyden_converges_and_batches_the_jacobian(sb, oracle, fixtures)
     rc, chk, x2, err2, jc2 = eng.broydn_device(x + 1e-4, 1e-8, jc=1)
     assert rc == 0 and np.abs(x2 - x).max() < 1e-5
     eng.close()
+
+
+@pytest.mark.parametrize("N,scale", [(33, 1.02), (65, 1.0), (129, 1.0)])
+def test_keep_trial_returns_the_field_whose_residual_is_reported(sb, oracle, fixtures, N, scale):
+    """SCFTB_BROYDN_KEEP_TRIAL: *err is the residual norm of the returned x (the reference flow may hand back the
+    previous iterate together with the trial's norm, broydn.c:215-228 / lnsrch.c)"""
+    x = oracle.mesh_uniform(33)
+    em = fixtures["n33_eta"][1:-1] * scale
+    Nc = 33
+    while Nc < N:
+        x, em = sb.refine_mesh(x, em)
+        Nc = 2 * Nc - 1
+    eng = sb.Engine(N, nsteps=2048, scheme=0, max_batch=N - 2)
+    rc, chk, xs, err, jc = eng.broydn_device(em, 1e-9, keep_trial=True)
+    assert rc == 0 and chk == 0 and err < 1e-9
+    assert abs(np.abs(eng.residual(xs)).max() - err) <= 1e-12
+    eng.close()
+
+
+def test_device_broyden_is_reproducible(sb, oracle, fixtures):
+    """the cooperative QR must not depend on block timing: repeated solves give the same bits"""
+    N = 257
+    x = oracle.mesh_uniform(33)
+    em = fixtures["n33_eta"][1:-1]
+    Nc = 33
+    while Nc < N:
+        x, em = sb.refine_mesh(x, em)
+        Nc = 2 * Nc - 1
+    eng = sb.Engine(N, nsteps=256, scheme=0, max_batch=N - 2)
+    runs = [eng.broydn_device(em, 1e-10) for _ in range(4)]
+    for r in runs[1:]:
+        assert r[1] == runs[0][1] and r[3] == runs[0][3] and np.array_equal(r[2], runs[0][2])
+    eng.close()
