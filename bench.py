@@ -306,7 +306,7 @@ def main():
                              "bytes_per_dof_step": BYTES_PER_DOF_STEP}}
         if not args.no_cpu_baseline and world == 1:
             cores = host_cores()
-            cnt = max(cores, 8) * 160   # ~10-20 s of CPU work
+            cnt = max(cores, 8) * 256   # ~10-20 s of CPU work (16 threads: 4096 problems in ~11 s)
             v, dt = oracle_throughput(cnt, cores)
             line["cpu_baseline"] = {"value": v, "unit": "DOF-steps/s", "cores": cores, "kind": "port",
                                     "sample": f"first {cnt} problems of the sweep, oracle/scft_oracle.c, {dt:.1f} s"}
