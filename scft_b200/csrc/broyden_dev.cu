@@ -306,8 +306,8 @@ __global__ void __launch_bounds__(BT) wfilter_kernel(int n, const double *fvec, 
 
 }  // namespace
 
-struct BroydenDev {
-  int n = 0, device = -1;
+struct BroydenDev {   // plays the role of the caller-owned globals qt, r, d (broydn.c:22-28): kept per engine across calls for jc
+  int n = 0;
   double *r = nullptr, *qt = nullptr, *xb = nullptr, *fb = nullptr, *vec = nullptr, *scal = nullptr;
   int *flags = nullptr;
   void release() {
@@ -316,7 +316,11 @@ struct BroydenDev {
     r = qt = xb = fb = vec = scal = nullptr; flags = nullptr; n = 0;
   }
 };
-static BroydenDev g_bd;   // plays the role of the caller-owned globals qt, r, d (broydn.c:22-28): kept across calls for jc
+static void free_broyden_state(void *p) {
+  BroydenDev *b = (BroydenDev *)p;
+  b->release();
+  delete b;
+}
 
 extern "C" int scftb_broydn_device(scftb_engine *e, double *x_host, int *check, double *err, int *jc) {
   return scftb_broydn_device_ex(e, x_host, check, err, jc, 0);
@@ -332,12 +336,14 @@ extern "C" int scftb_broydn_device_ex(scftb_engine *e, double *x_host, int *chec
   cudaStream_t st = e->stream;
   int rc = upload_params(e);
   if (rc) return rc;
-  if (g_bd.n != n || g_bd.device != e->cfg.device) {
+  if (!e->solver_state) { e->solver_state = new BroydenDev(); e->solver_state_free = free_broyden_state; }
+  BroydenDev &g_bd = *(BroydenDev *)e->solver_state;
+  if (g_bd.n != n) {
     g_bd.release();
     const size_t nn = (size_t)n * n;
     CK(cudaMalloc(&g_bd.r, 8 * nn)); CK(cudaMalloc(&g_bd.qt, 8 * nn)); CK(cudaMalloc(&g_bd.xb, 8 * nn)); CK(cudaMalloc(&g_bd.fb, 8 * nn));
     CK(cudaMalloc(&g_bd.vec, 8 * (size_t)n * 12)); CK(cudaMalloc(&g_bd.scal, 8 * 16)); CK(cudaMalloc(&g_bd.flags, sizeof(int) * 4));
-    g_bd.n = n; g_bd.device = e->cfg.device;
+    g_bd.n = n;
     *jc = 0;
   }
   double *r = g_bd.r, *qt = g_bd.qt, *V = g_bd.vec;

@@ -305,6 +305,7 @@ int scftb_destroy(scftb_engine *e) {
   scftb_unbind_engine(e);
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
+  if (e->solver_state && e->solver_state_free) e->solver_state_free(e->solver_state);
   for (double *p : {e->d_eta, e->d_out, e->d_phi, e->d_Q, e->d_f0, e->d_L, e->d_x, e->d_eta_bnd, e->d_w, e->d_hist,
                     e->d_eta_full, e->d_scratch})
     if (p) cudaFree(p);

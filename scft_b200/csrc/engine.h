@@ -54,6 +54,9 @@ struct scftb_engine {
   // optional per-launch timing of the march kernel (CUDA events on the launching stream)
   bool timing;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+  // state a device-resident solver keeps between calls on this engine (Broyden's QR factors for jc), with its deleter
+  void *solver_state = nullptr;
+  void (*solver_state_free)(void *) = nullptr;
 };
 
 namespace scftb {

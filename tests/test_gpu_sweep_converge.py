@@ -33,3 +33,12 @@ def test_continuation_rejects_unreachable_target():
     from scft_b200 import sweep
     with pytest.raises(ValueError):
         sweep.Continuation(N_target=100, N0=33)
+
+
+def test_threaded_block_equals_serial(fixtures):
+    """host threads only overlap independent problems: same rows as the serial loop"""
+    from scft_b200 import sweep
+    eta33 = fixtures["n33_eta"][1:-1]
+    a = sweep.converge_block(3, 9, eta33, N_target=65, threads=1)
+    b = sweep.converge_block(3, 9, eta33, N_target=65, threads=3)
+    assert np.all(a[:, 0] == 0) and np.array_equal(a[:, :4], b[:, :4])

@@ -1,6 +1,6 @@
 """Time-to-converge of the 4096-problem sweep, measured on a bounded sample.
 
-  python tools/sweep_converge.py [problems_per_rank=32] [N_target=1025]
+  python tools/sweep_converge.py [problems_per_rank=32] [N_target=1025] [host_threads=1]
   python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/sweep_converge.py 32
 
 Each rank converges the first `problems_per_rank` problems of its block of the sweep (consecutive problems walk
@@ -21,6 +21,7 @@ from scft_b200 import sweep  # noqa: E402
 def main():
     count = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     N_target = int(sys.argv[2]) if len(sys.argv) > 2 else 1025
+    threads = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
@@ -32,9 +33,8 @@ def main():
     eta33 = fx["n33_eta"][1:-1]  # DEALII_SCFT/inputFiles/N=33_for_read.txt (the reference's own start, drivescft.cc:264)
     total = 4096
     p0, p1 = sweep.shard(total, rank, world)
-    t0 = time.perf_counter()
-    rows = sweep.converge_block(p0, p0 + count, eta33, N_target=N_target, device=local)
-    wall = time.perf_counter() - t0
+    rows = sweep.converge_block(p0, p0 + count, eta33, N_target=N_target, device=local, threads=threads)
+    wall = sweep.converge_block.last_wall
     full = sweep.gather_results(np.hstack([rows, np.full((count, 1), wall)]), count * world, rank, world) \
         if world > 1 else np.hstack([rows, np.full((count, 1), wall)])
     if rank == 0:
@@ -47,8 +47,9 @@ def main():
         print(f"  F range {np.nanmin(full[:, 2]):.6e} .. {np.nanmax(full[:, 2]):.6e}, Q range "
               f"{np.nanmin(full[:, 3]):.6f} .. {np.nanmax(full[:, 3]):.6f}")
         per_rank = total // world
-        print(f"  extrapolated to the whole sweep: {per_rank} problems per GPU x {sec.mean():.3f} s = "
-              f"{per_rank * sec.mean() / 60:.1f} min on {world} GPU(s)")
+        rate = count / full[:, 5].max()
+        print(f"  {threads} host thread(s) per GPU: {rate:.2f} problems/s per GPU; extrapolated to the whole sweep: "
+              f"{per_rank} problems per GPU / {rate:.2f} per s = {per_rank / rate / 60:.1f} min on {world} GPU(s)")
         for i in np.flatnonzero(~ok)[:8]:
             print(f"  not converged: sample {i} check {int(full[i, 0])} err {full[i, 1]:.2e}")
     if world > 1:
