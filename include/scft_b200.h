@@ -129,6 +129,24 @@ int scftb_broydn_device(scftb_engine *e, double *x, int *check, double *err, int
 #define SCFTB_BROYDN_KEEP_TRIAL 1
 int scftb_broydn_device_ex(scftb_engine *e, double *x, int *check, double *err, int *jc, int flags);
 
+/* ---- two-species (AB diblock) extension: q and q+ as separate sweeps ------------------------------
+ * Not in the reference (its melt is one species and uses q+(x,s) = q(x,1-s), drivescft.cc:189-190); it is the
+ * diblock model of WQ-HardSurf.pdf II.B that gives sweeps their chi N axis.  The chain has an A
+ * block of fraction fA (fA*nsteps must be an integer number of contour steps) and a B block; q is marched from the
+ * A end and q+ from the B end with the engine's implicit-Euler scheme, every slice of q is kept in HBM and the
+ * q+ sweep accumulates phi_A = int_0^fA q q+ ds and phi_B = int_fA^1 q q+ ds on the fly (the engine's quadrature
+ * on every block that has 2^k >= 16 steps, else the trapezoid rule).  Unknowns and residual of problem p:
+ *     w[2][N-2]   = (eta_A, eta_B) on the interior nodes
+ *     out[2][N-2] = ( sign*(phi_0 - phi_A - phi_B),  eta_A - eta_B - chiN*(phi_B - phi_A) )
+ * (same gauge as the reference residual: no 1/Q).  With eta_A == eta_B the first half is the reference residual.
+ * scftb_set_diblock: fA is a property of the engine, chiN of problem p (all problems when p < 0). */
+int scftb_set_diblock(scftb_engine *e, int p, double fA, double chiN);
+int scftb_residual_ab(scftb_engine *e, const double *w, double *out);
+int scftb_residual_ab_batch(scftb_engine *e, int nprob, const double *w, double *out);
+int scftb_get_phi_ab(scftb_engine *e, int p, double *phiA, double *phiB);
+/* residual callback of the bound engine for the generic solvers, n = 2*(N-2), 0-based */
+void scftb_callback_ab_c0(int n, double *in, double *out);
+
 /* Device-resident batched Anderson mixing (adm_chen semantics) on the engine's problems:
  * x[nprob][N-2] host in/out.  All nprob problems iterate in lock-step, each with its own
  * history, Gram matrix, gaussj solve and relaxation; nothing but the per-problem error norms

@@ -65,6 +65,9 @@ def lib():
         L.orc_eta_full.argtypes = [C.c_int, _dp, _dp, _dp]
         L.orc_residual.restype = C.c_int
         L.orc_residual.argtypes = [C.POINTER(Config), _dp, _dp, _dp, _dp, _dp, _dp]
+        L.orc_residual_ab.restype = C.c_int
+        L.orc_residual_ab.argtypes = [C.POINTER(Config), _dp, _dp, C.c_int, C.c_double, _dp, _dp, _dp, _dp,
+                                      C.POINTER(C.c_double)]
         L.orc_free_energy.restype = C.c_double
         L.orc_free_energy.argtypes = [C.c_int, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int]
         L.orc_gaussj.restype = C.c_int
@@ -136,6 +139,21 @@ def residual(eta_full_, f0, scheme=IE_CONSISTENT, nsteps=2048, L=L_REF, x=None, 
     if want_hist:
         r["hist"] = hist
     return r
+
+
+def residual_ab(etaA_full, etaB_full, jf, chiN, f0, scheme=IE_ROWSCALE, nsteps=2048, L=L_REF, x=None,
+                quadrature=QUAD_ROMBERG, sign=1.0):
+    """Two-species residual (orc_residual_ab): dict(out[2*(N-2)], phiA, phiB, Q)."""
+    a, b, f0 = _arr(etaA_full), _arr(etaB_full), _arr(f0)
+    N = len(a)
+    xa = None if x is None else _arr(x)
+    cfg = Config(scheme, N, nsteps, quadrature, sign, L, _p(xa) if xa is not None else None)
+    out, pa, pb, Q = np.zeros(2 * (N - 2)), np.zeros(N), np.zeros(N), C.c_double(0)
+    rc = lib().orc_residual_ab(C.byref(cfg), _p(a), _p(b), int(jf), float(chiN), _p(f0), _p(out), _p(pa), _p(pb),
+                               C.byref(Q))
+    if rc:
+        raise ValueError("orc_residual_ab: IE schemes only, 0 < jf < nsteps")
+    return dict(out=out, phiA=pa, phiB=pb, Q=Q.value)
 
 
 def free_energy(x, eta_full_, tau=TAU_REF, L=L_REF, f0bar_=0.892581217773656, nplot=(1 << 18) + 1):

@@ -362,6 +362,108 @@ int orc_residual(const orc_config *cfg, const double *eta, const double *f0_give
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Two-species (AB diblock) extension, SURVEY.md section 8(f)-4.  NOT in the reference: the
+ * reference melt is one species and uses q+(x,s) = q(x,1-s) (drivescft.cc:189-190).  Here the
+ * chain has an A block (contour steps 1..jf, field eta_A) and a B block (steps jf+1..n, field
+ * eta_B); q is marched from the A end, q+ from the B end, each with the implicit-Euler step of
+ * orc_residual, and
+ *     phi_A(x) = int_0^f q(x,s) q+(x,1-s) ds,   phi_B(x) = int_f^1 q(x,s) q+(x,1-s) ds
+ * with the reference's quadrature on each block (Romberg when the block has 2^k >= 16 steps,
+ * else the trapezoid rule of simple_FEM_1D_transient.m:120-124).  Residual, same gauge as the
+ * reference (no 1/Q):   out[0..ni)   = sign*(phi_0 - phi_A - phi_B)         incompressibility
+ *                       out[ni..2ni) = eta_A - eta_B - chiN*(phi_B - phi_A)  exchange
+ * With eta_A == eta_B both sweeps coincide and phi_A + phi_B is the one-sweep density.
+ * PARITY PINNED BY ORACLE ONLY.
+ * ------------------------------------------------------------------------------------------ */
+static band_t *ie_system(const orc_config *cfg, const double *x, const double *eta, double *Al, double *Ad,
+                         double *Au) {
+  const int N = cfg->N, n = cfg->nsteps, ni = N - 2;
+  const double dt = 1. / n, hU = cfg->L / (N - 1);
+  const int uniform = (cfg->x == NULL);
+  band_t *S = band_new(ni, 1, 1);
+  for (int i = 1; i <= N - 2; i++) {
+    double a1 = uniform ? hU : x[i] - x[i - 1], a2 = uniform ? hU : x[i + 1] - x[i];
+    double bl, bd, bu, cl, cd, cu;
+    if (uniform) { Al[i] = hU / 6; Ad[i] = 2. / 3 * hU; Au[i] = hU / 6; bl = -1 / hU; bd = 2. / hU; bu = -1 / hU; }
+    else { Al[i] = a1 / 6; Ad[i] = a1 / 3 + a2 / 3; Au[i] = a2 / 6; bl = -1 / a1; bd = 1 / a1 + 1 / a2; bu = -1 / a2; }
+    if (cfg->scheme == ORC_IE_ROWSCALE) { cl = Al[i] * eta[i]; cd = Ad[i] * eta[i]; cu = Au[i] * eta[i]; }
+    else {
+      cl = a1 * (eta[i - 1] + eta[i]) / 12;
+      cu = a2 * (eta[i] + eta[i + 1]) / 12;
+      cd = a1 * (eta[i - 1] + 3 * eta[i]) / 12 + a2 * (3 * eta[i] + eta[i + 1]) / 12;
+    }
+    int r = i - 1;
+    if (i > 1) band_set(S, r, r - 1, Al[i] + dt * (bl + cl));
+    band_set(S, r, r, Ad[i] + dt * (bd + cd));
+    if (i < N - 2) band_set(S, r, r + 1, Au[i] + dt * (bu + cu));
+  }
+  band_factor(S);
+  return S;
+}
+
+static double quad_block(const orc_config *cfg, const double *v, int m, double h) {
+  if (cfg->quadrature == ORC_QUAD_ROMBERG && m >= 16 && (m & (m - 1)) == 0) return orc_romint(v, m, h);
+  double s = 0;
+  for (int j = 0; j < m; j++) s = s + 0.5 * (v[j] + v[j + 1]) * h;
+  return s;
+}
+
+int orc_residual_ab(const orc_config *cfg, const double *etaA, const double *etaB, int jf, double chiN,
+                    const double *f0_given, double *out, double *phiA_out, double *phiB_out, double *Q_out) {
+  const int N = cfg->N, n = cfg->nsteps, ni = N - 2;
+  if (cfg->scheme == ORC_IRK4_CONSISTENT || jf < 1 || jf >= n) return 1;
+  double *x = (double *)malloc(sizeof(double) * N);
+  mesh_coords(cfg, x);
+  const int uniform = (cfg->x == NULL);
+  const double hU = cfg->L / (N - 1);
+  double *Al = calloc(N, 8), *Ad = calloc(N, 8), *Au = calloc(N, 8);
+  band_t *SA = ie_system(cfg, x, etaA, Al, Ad, Au);
+  band_t *SB = ie_system(cfg, x, etaB, Al, Ad, Au);   /* the mass matrix does not depend on the field */
+  double *hq = (double *)calloc((size_t)N * (n + 1), sizeof(double));
+  double *hd = (double *)calloc((size_t)N * (n + 1), sizeof(double));
+  double *q = calloc(N, 8), *rhs = calloc(N, 8);
+  double Q = 0;
+  for (int sweep = 0; sweep < 2; sweep++) {
+    double *H = sweep == 0 ? hq : hd;
+    for (int i = 0; i < N; i++) q[i] = (i >= 1 && i <= N - 2) ? 1.0 : 0.0;
+    for (int i = 0; i < N; i++) H[(size_t)i * (n + 1)] = q[i];
+    for (int step = 1; step <= n; step++) {
+      /* forward: A block first; backward: B block first */
+      const band_t *S = (sweep == 0) ? (step <= jf ? SA : SB) : (step <= n - jf ? SB : SA);
+      for (int i = 1; i <= N - 2; i++) rhs[i - 1] = Al[i] * q[i - 1] + Ad[i] * q[i] + Au[i] * q[i + 1];
+      band_solve(S, rhs);
+      for (int i = 1; i <= N - 2; i++) { q[i] = rhs[i - 1]; H[(size_t)i * (n + 1) + step] = q[i]; }
+    }
+    if (sweep == 0) {
+      double s = 0;
+      for (int i = 1; i <= N - 2; i++) {
+        double a1 = uniform ? hU : x[i] - x[i - 1], a2 = uniform ? hU : x[i + 1] - x[i];
+        s += 0.5 * (a1 + a2) * q[i];
+      }
+      Q = s / (uniform ? cfg->L : (x[N - 1] - x[0]));
+    }
+  }
+  double *v = (double *)malloc(sizeof(double) * (n + 1));
+  double *pa = calloc(N, 8), *pb = calloc(N, 8);
+  for (int i = 0; i < N; i++) {
+    for (int j = 0; j <= n; j++) v[j] = hq[(size_t)i * (n + 1) + j] * hd[(size_t)i * (n + 1) + (n - j)];
+    pa[i] = quad_block(cfg, v, jf, 1. / n);
+    pb[i] = quad_block(cfg, v + jf, n - jf, 1. / n);
+  }
+  if (out)
+    for (int i = 1; i <= N - 2; i++) {
+      out[i - 1] = cfg->sign * (f0_given[i] - pa[i] - pb[i]);
+      out[ni + i - 1] = etaA[i] - etaB[i] - chiN * (pb[i] - pa[i]);
+    }
+  if (phiA_out) memcpy(phiA_out, pa, sizeof(double) * N);
+  if (phiB_out) memcpy(phiB_out, pb, sizeof(double) * N);
+  if (Q_out) *Q_out = Q;
+  band_free(SA); band_free(SB);
+  free(x); free(Al); free(Ad); free(Au); free(hq); free(hd); free(q); free(rhs); free(v); free(pa); free(pb);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Free energy (scft.cc:271-291 resample + :404-450 Romberg).
  * ------------------------------------------------------------------------------------------ */
 double orc_free_energy(int N, const double *x, const double *eta, double tau, double L, double f0bar,

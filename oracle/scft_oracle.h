@@ -71,6 +71,12 @@ void orc_eta_full(int N, const double *x, const double *eta_mid, double *eta_ful
 int orc_residual(const orc_config *cfg, const double *eta_full, const double *f0_given,
                  double *out_mid, double *phi, double *q_hist, double *Q);
 
+/* Two-species (AB diblock) extension of the residual — not in the reference, parity by oracle only.
+ * etaA/etaB: N values each (full fields); jf: contour steps of the A block (0 < jf < nsteps);
+ * out[2*(N-2)]: sign*(phi0 - phiA - phiB) then etaA - etaB - chiN*(phiB - phiA); IE schemes only. */
+int orc_residual_ab(const orc_config *cfg, const double *etaA, const double *etaB, int jf, double chiN,
+                    const double *f0_given, double *out, double *phiA, double *phiB, double *Q);
+
 /* Mean-field free energy per segment (scft.cc:404-450 via :271-291). */
 double orc_free_energy(int N, const double *x, const double *eta_full, double tau, double L,
                        double f0bar, int nplot);

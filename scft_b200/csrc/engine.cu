@@ -117,6 +117,12 @@ __global__ void spline_bnd_kernel(int nprob, int N, const double *x, const doubl
   }
 }
 
+void spline_bnd_launch(int nprob, int N, const double *x, const double *eta_mid, long long eta_stride, double *scratch,
+                       double *eta_bnd, cudaStream_t st) {
+  spline_bnd_kernel<<<(nprob + 63) / 64, 64, 0, st>>>(nprob, N, x, eta_mid, eta_stride, scratch, eta_bnd);
+  g_launches++;
+}
+
 // ---------------------------------------------------------------------------------------------
 template <int C, int T, int MINB>
 static march_fn pick(bool uni, bool odd) {
@@ -306,6 +312,7 @@ int scftb_destroy(scftb_engine *e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   if (e->solver_state && e->solver_state_free) e->solver_state_free(e->solver_state);
+  if (e->diblock_state && e->diblock_state_free) e->diblock_state_free(e->diblock_state);
   for (double *p : {e->d_eta, e->d_out, e->d_phi, e->d_Q, e->d_f0, e->d_L, e->d_x, e->d_eta_bnd, e->d_w, e->d_hist,
                     e->d_eta_full, e->d_scratch})
     if (p) cudaFree(p);
@@ -341,7 +348,7 @@ int scftb_set_problem(scftb_engine *e, int p, double tau, double L, const double
 namespace scftb {
 int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_stride, double *d_out,
                  long long out_stride, const int *d_skip, cudaStream_t st) {
-  MarchParams P;
+  MarchParams P{};
   P.N = e->cfg.N; P.ni = e->ni; P.nsteps = e->cfg.nsteps;
   P.scheme = e->cfg.scheme; P.nprob = nprob; P.store_full = e->cfg.store_history;
   P.uniform = e->uniform ? 1 : 0; P.sign = e->cfg.sign;

@@ -26,6 +26,8 @@ struct KernelChoice {
 };
 extern std::atomic<long> g_launches;
 int choose_kernel(int ni, bool uni, KernelChoice &kc, bool odd);
+void spline_bnd_launch(int nprob, int N, const double *x, const double *eta_mid, long long eta_stride, double *scratch,
+                       double *eta_bnd, cudaStream_t st);
 }  // namespace scftb
 
 #define CK(call)                                                                                   \
@@ -57,6 +59,9 @@ struct scftb_engine {
   // state a device-resident solver keeps between calls on this engine (Broyden's QR factors for jc), with its deleter
   void *solver_state = nullptr;
   void (*solver_state_free)(void *) = nullptr;
+  // two-species extension (diblock.cu): its buffers, with their deleter
+  void *diblock_state = nullptr;
+  void (*diblock_state_free)(void *) = nullptr;
 };
 
 namespace scftb {

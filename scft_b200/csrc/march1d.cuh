@@ -52,6 +52,12 @@ struct MarchParams {
   double *phi;            // [nprob][N]
   double *Q;              // [nprob]
   double *eta_full;       // [nprob][N] (diagnostic, scft.cc:452-490) or nullptr
+  // two-species instantiation only (TWO = true): fields [nprob][2][ni] in eta_mid (eta_stride >= 2 ni)
+  int jf;                 // contour steps of the A block, 0 < jf < nsteps
+  const double *wA, *wB;  // [nsteps+1] block quadrature weights over the contour index (zero outside the block)
+  const double *chi;      // [nprob] chi N
+  const double *eta_bndB; // [nprob][2] wall values of the B field (non-uniform) or nullptr
+  double *phiB;           // [nprob][N]
 };
 
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
@@ -84,10 +90,10 @@ __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_g
 // eta on node i (0..N-1).  Wall nodes: natural-spline extrapolation of the interior values
 // (scft.cc:456-475 -> spline_chen.c:77-100).  With y''=0 at the end knots the cubic term of the
 // first/last piece vanishes on a uniform mesh, leaving the linear extrapolation a*y0+b*y1.
-__device__ __forceinline__ double eta_node(const MarchParams &P, int p, int i, double L) {
-  const double *em = P.eta_mid + (size_t)p * P.eta_stride;
+__device__ __forceinline__ double eta_node(const MarchParams &P, int p, int i, double L, bool fieldB = false) {
+  const double *em = P.eta_mid + (size_t)p * P.eta_stride + (fieldB ? P.ni : 0);
   if (i >= 1 && i <= P.N - 2) return em[i - 1];
-  if (!P.uniform) return P.eta_bnd[2 * p + (i == 0 ? 0 : 1)];
+  if (!P.uniform) return (fieldB ? P.eta_bndB : P.eta_bnd)[2 * p + (i == 0 ? 0 : 1)];
   const int N = P.N;
   if (i == 0) {
     double x0 = L * 0 / (N - 1), x1 = L * 1 / (N - 1), x2 = L * 2 / (N - 1);
@@ -102,7 +108,7 @@ __device__ __forceinline__ double eta_node(const MarchParams &P, int p, int i, d
 struct Row { double Al, Ad, Au, Tl, Td, Tu, Dl, Dd, Du; };   // A (mass), T = A + dt*D, D = B + C
 
 // Row g (0-based interior index) of A (mass) and T = A + ds*(B + C).
-__device__ __forceinline__ Row assemble_row(const MarchParams &P, int p, int g, double L, double dt) {
+__device__ __forceinline__ Row assemble_row(const MarchParams &P, int p, int g, double L, double dt, bool fieldB = false) {
   Row r;
   if (g >= P.ni) { r.Al = r.Ad = r.Au = 0.0; r.Tl = r.Tu = 0.0; r.Td = 1.0; r.Dl = r.Du = 0.0; r.Dd = 0.0; return r; }  // padding
   const int i = g + 1;
@@ -118,11 +124,11 @@ __device__ __forceinline__ Row assemble_row(const MarchParams &P, int p, int g, 
     r.Al = a1 / 6; r.Ad = a1 / 3 + a2 / 3; r.Au = a2 / 6;
     bl = -1 / a1; bd = 1 / a1 + 1 / a2; bu = -1 / a2;
   }
-  double e0 = eta_node(P, p, i, L), cl, cd, cu;
+  double e0 = eta_node(P, p, i, L, fieldB), cl, cd, cu;
   if (P.scheme == 0) {  // row-scaled lumping, 1D_FEM.c:104-105
     cl = r.Al * e0; cd = r.Ad * e0; cu = r.Au * e0;
   } else {              // (eta_h phi_i, phi_j), 2-point Gauss exact for linear eta_h (scft.cc:653-655)
-    double em = eta_node(P, p, i - 1, L), ep = eta_node(P, p, i + 1, L);
+    double em = eta_node(P, p, i - 1, L, fieldB), ep = eta_node(P, p, i + 1, L, fieldB);
     cl = a1 * (em + e0) / 12;
     cu = a2 * (e0 + ep) / 12;
     cd = a1 * (em + 3 * e0) / 12 + a2 * (3 * e0 + ep) / 12;
@@ -147,7 +153,11 @@ constexpr int PUB = 8;  // doubles per warp in a publish buffer: [0] qf, [1] zf,
 
 // ODDN: instantiation for an odd number of contour steps (only then the first pairing step needs its partner slice
 // re-read; keeping it out of the even-n instantiation leaves the hot loop's register allocation untouched)
-template <int C, int T, bool UNI, int MINB, bool ODDN>
+// TWO: two-species (AB diblock) instantiation, SURVEY.md section 8(f)-4 — not in the reference.  The march runs as four
+// segments, each with its own assembly + factor setup: q forward through the A block (field A, steps 1..jf) and the B block
+// (field B), every slice stored; then q+ backward through the B block and the A block, every step paired with the stored
+// slice q(n-j) and accumulated into phi_A / phi_B with the block weights.  TWO = false is the reference's one-sweep form.
+template <int C, int T, bool UNI, int MINB, bool ODDN, bool TWO = false>
 __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
   static_assert(C == 1 || (C % 2) == 0, "C must be 1 or even");
   constexpr int CI = C - 1;             // chunk-interior nodes per thread
@@ -171,12 +181,20 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
   for (int p = blockIdx.x; p < P.nprob; p += gridDim.x) {
     if (P.skip && P.skip[p]) continue;
     const double L = P.L[p];
+    // state that lives across the segments of a two-species march (one segment otherwise)
+    double q[C], phi[C], phiB[TWO ? C : 1];
+    double XL, qn, qsumF = 0.0;
+    double *hw;
+    const double *hr;
+    for (int seg = 0; seg < (TWO ? 4 : 1); seg++) {
+    const bool fB = TWO && (seg == 1 || seg == 2);        // field of this segment
+    const bool backward = TWO && seg >= 2;                // q+ sweep
     // ------------------------------------------------------------------ assembly + level 1
     double ca[CA], cd[CA], cu[CA];      // pre-scaled rows of A on chunk-interior nodes (UNI: ca==cu)
     double al[CA], be[CA], gl[CA], gr[CA];
     double sAl, sAd, sAu, sl, sd, su;   // separator row of A and T
     {
-      Row rs = assemble_row(P, p, t * C + CI, L, dt);
+      Row rs = assemble_row(P, p, t * C + CI, L, dt, fB);
       sAl = rs.Al; sAd = rs.Ad; sAu = rs.Au; sl = rs.Tl; sd = rs.Td; su = rs.Tu;
       // UNI: A's separator row is A_off * (1, 4, 1); the Dirichlet zeroing is carried by the neighbour
       // values (exactly 0 on walls / padding), so one coefficient is kept (in sAd)
@@ -190,7 +208,7 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
       double ulo[CA];                           // pinv_k * Tu_k (setup only)
 #pragma unroll
       for (int k = CI - 1; k >= 0; k--) {
-        Row r = assemble_row(P, p, t * C + k, L, dt);
+        Row r = assemble_row(P, p, t * C + k, L, dt, fB);
         double piv = (k == CI - 1) ? r.Td : r.Td - (r.Tu * pinv_next) * Tl_next;
         double pinv = 1.0 / piv;
         // UNI: one off-diagonal coefficient serves both neighbours; the Dirichlet zeroing of A is
@@ -326,15 +344,21 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     // only when they are few
     // ------------------------------------------------------------------ initial condition
     // q = 1 on interior nodes, 0 on walls / padding (drivescft.cc:120-127, 1D_FEM.c:114-129)
-    double q[C], phi[C];
+    const bool sweep_start = !TWO || seg == 0 || seg == 2;
+    if (sweep_start) {
 #pragma unroll
-    for (int k = 0; k < C; k++) { q[k] = (t * C + k < P.ni) ? 1.0 : 0.0; phi[k] = 0.0; }
-    double XL = (t > 0 && t * C - 1 < P.ni) ? 1.0 : 0.0;   // value at the left separator
-    double qn = ((t + 1) * C < P.ni) ? 1.0 : 0.0;          // first node of the next chunk
-    double *hb = P.hist + (size_t)(P.store_full ? p : blockIdx.x) * P.hist_stride;
-    // per-thread view of a slice: C == 1: doubles at [t]; else double2 at [(k/2)*T + t]
-    double *hw = hb + ((C == 1) ? t : 2 * t);               // write cursor (slice j)
-    const double *hr = hw + (size_t)n * SL;                 // read cursor (slice n-j)
+      for (int k = 0; k < C; k++) q[k] = (t * C + k < P.ni) ? 1.0 : 0.0;
+      XL = (t > 0 && t * C - 1 < P.ni) ? 1.0 : 0.0;   // value at the left separator
+      qn = ((t + 1) * C < P.ni) ? 1.0 : 0.0;          // first node of the next chunk
+      double *hb = P.hist + (size_t)(P.store_full ? p : blockIdx.x) * P.hist_stride;
+      // per-thread view of a slice: C == 1: doubles at [t]; else double2 at [(k/2)*T + t]
+      hw = hb + ((C == 1) ? t : 2 * t);               // write cursor (slice j)
+      hr = hw + (size_t)n * SL;                       // read cursor (slice n-j)
+    }
+    if (!TWO || seg == 0) {
+#pragma unroll
+      for (int k = 0; k < C; k++) { phi[k] = 0.0; if (TWO) phiB[k] = 0.0; }
+    }
     auto store_slice = [&](double *dst) {
       if constexpr (C == 1) dst[0] = q[0];
       else {
@@ -342,7 +366,7 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
         for (int k = 0; k < C; k += 2) *reinterpret_cast<double2 *>(dst + k * T) = make_double2(q[k], q[k + 1]);
       }
     };
-    store_slice(hw);
+    if (!TWO || seg == 0) store_slice(hw);
     const double *wq = P.w;
     const bool full = P.store_full != 0;
 
@@ -357,7 +381,7 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     const double mW = s_minv[wid][v3], mM = (wid > 0) ? s_minv[(wid + NW - 1) % NW][v3] : 0.0;
     const int g8 = lane & 7;
     auto prefetch = [&](int jj, const double *src) {   // slice n-jj -> staging buffer jj&1
-      if (STAGE && 2 * jj > n && jj <= n) {
+      if (STAGE && (TWO ? backward : 2 * jj > n) && jj <= n) {
         const unsigned dst = qo_me + (jj & 1) * QO_BUF;
         if constexpr (C == 1) cp_async8(dst, src);
         else {
@@ -367,12 +391,24 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
       }
       if (STAGE) cp_async_commit();
     };
-    prefetch(1, hr - SL);
+    if (TWO && seg == 2) {   // q+(., 0) = 1 pairs with the last slice of q (plain loads: stored by this thread)
+      const double wa = __ldg(P.wA + n), wb = __ldg(P.wB + n);
+#pragma unroll
+      for (int k = 0; k < C; k++) {
+        const double v = hr[(C == 1) ? 0 : (k / 2) * 2 * T + (k & 1)] * q[k];
+        phi[k] = fma(wa, v, phi[k]);
+        phiB[TWO ? k : 0] = fma(wb, v, phiB[TWO ? k : 0]);
+      }
+    }
+    if (sweep_start) prefetch(1, hr - SL);
+    // contour steps of this segment
+    const int jbeg = !TWO ? 1 : (seg == 0 ? 1 : (seg == 1 ? P.jf + 1 : (seg == 2 ? 1 : n - P.jf + 1)));
+    const int jend = !TWO ? n : (seg == 0 ? P.jf : (seg == 1 ? n : (seg == 2 ? n - P.jf : n)));
 
     // ------------------------------------------------------------------ the contour march
-    for (int j = 1; j <= n; j++) {
+    for (int j = jbeg; j <= jend; j++) {
       hw += SL; hr -= SL;
-      const bool pairing = (2 * j > n);
+      const bool pairing = TWO ? backward : (2 * j > n);
       // the slice the NEXT step pairs with is fetched a whole step ahead.  For odd n the first pairing step
       // (j = (n+1)/2) pairs with the slice stored one step earlier, which was not written yet when its prefetch
       // was issued: once, copy it into the staging buffer with ordinary loads (ordered after this thread's store)
@@ -476,6 +512,26 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
       qn = shfl_dn_d(q[0], 1);
       qn = (lane == 31) ? 0.0 : qn;   // supplied through the publish buffer
       // history + fused quadrature
+      if constexpr (TWO) {
+        if (!backward) store_slice(hw);
+        else {
+          const double wa = __ldg(P.wA + (n - j)), wb = __ldg(P.wB + (n - j));   // weights of the q slice's contour index
+          if (STAGE) cp_async_wait1();
+          const unsigned src = qo_me + (j & 1) * QO_BUF;
+          if constexpr (C == 1) {
+            const double v = (STAGE ? lds64(src) : hr[0]) * q[0];
+            phi[0] = fma(wa, v, phi[0]); phiB[0] = fma(wb, v, phiB[0]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < C; k += 2) {
+              const double2 v = STAGE ? lds128(src + (k / 2) * T * 16) : *reinterpret_cast<const double2 *>(hr + k * T);
+              const double v0 = v.x * q[k], v1 = v.y * q[k + 1];
+              phi[k] = fma(wa, v0, phi[k]); phiB[TWO ? k : 0] = fma(wb, v0, phiB[TWO ? k : 0]);
+              phi[k + 1] = fma(wa, v1, phi[k + 1]); phiB[TWO ? k + 1 : 0] = fma(wb, v1, phiB[TWO ? k + 1 : 0]);
+            }
+          }
+        }
+      } else {
       if (full || 2 * j < n) store_slice(hw);
       if (2 * j >= n) {
         const double wj = __ldg(wq + j);   // j > n/2: 2*w_j (pair j, n-j); j == n/2: w_j
@@ -496,10 +552,46 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
           for (int k = 0; k < C; k++) phi[k] = fma(wj * q[k], q[k], phi[k]);
         }
       }
+      }
     }
+    if (TWO && seg == 1) {   // Q = (1/L) int q(x,1) dx from the forward sweep
+#pragma unroll
+      for (int k = 0; k < C; k++) {
+        const int g = t * C + k;
+        if (g < P.ni) {
+          const int i = g + 1;
+          double hw2;
+          if (P.uniform) { double h = L / (P.N - 1); hw2 = 0.5 * (h + h); }
+          else { const double *x = P.x + (size_t)p * P.N; hw2 = 0.5 * ((x[i] - x[i - 1]) + (x[i + 1] - x[i])); }
+          qsumF += hw2 * q[k];
+        }
+      }
+    }
+    }   // segments
 
     // ------------------------------------------------------------------ residual, phi, Q
     double qsum = 0.0;
+    if constexpr (TWO) {
+      const double chi = P.chi[p];
+      const double *em = P.eta_mid + (size_t)p * P.eta_stride;
+#pragma unroll
+      for (int k = 0; k < C; k++) {
+        const int g = t * C + k;
+        if (g < P.ni) {
+          const int i = g + 1;
+          const double f0 = P.f0[(size_t)p * P.N + i], pa = phi[k], pb = phiB[TWO ? k : 0];
+          P.out[(size_t)p * P.out_stride + g] = P.sign * (f0 - pa - pb);
+          P.out[(size_t)p * P.out_stride + P.ni + g] = em[g] - em[P.ni + g] - chi * (pb - pa);
+          P.phi[(size_t)p * P.N + i] = pa;
+          P.phiB[(size_t)p * P.N + i] = pb;
+        }
+      }
+      if (t == 0) {
+        P.phi[(size_t)p * P.N] = 0.0; P.phi[(size_t)p * P.N + P.N - 1] = 0.0;
+        P.phiB[(size_t)p * P.N] = 0.0; P.phiB[(size_t)p * P.N + P.N - 1] = 0.0;
+      }
+      qsum = qsumF;
+    } else {
 #pragma unroll
     for (int k = 0; k < C; k++) {
       const int g = t * C + k;
@@ -521,6 +613,7 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
         P.eta_full[(size_t)p * P.N] = eta_node(P, p, 0, L);
         P.eta_full[(size_t)p * P.N + P.N - 1] = eta_node(P, p, P.N - 1, L);
       }
+    }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, d);

@@ -87,6 +87,12 @@ void scftb_callback_c0(int n, double *in, double *out) {
 
 void scftb_callback_nr1(int n, double *in, double *out) { scftb_callback_c0(n, in + 1, out + 1); }
 
+// two-species residual of the bound engine (n = 2*(N-2) unknowns: eta_A, eta_B)
+void scftb_callback_ab_c0(int n, double *in, double *out) {
+  (void)n;
+  if (!g_bound || scftb_residual_ab(g_bound, in, out) != SCFTB_OK) scftb_funcerr = 1;
+}
+
 void scftb_callback_fixedpoint_c0(int n, double *in, double *out) {
   scftb_callback_c0(n, in, out);
   for (int i = 0; i < n; i++) out[i] += in[i];
@@ -336,6 +342,14 @@ extern "C" int scftb_broydn(scftb_func vecfunc, double *x, int n, int *check, do
         for (int j0 = 0; j0 < n && batched; j0 += B) {
           int nb = std::min(B, n - j0);
           if (scftb_residual_batch(g_bound, nb, &xb[(size_t)j0 * n], &fb[(size_t)j0 * n]) != SCFTB_OK) { scftb_funcerr = 1; }
+        }
+      }
+      if (vecfunc == scftb_callback_ab_c0 && g_bound) {   // two-species: the 2(N-2) columns in device batches
+        batched = true;
+        int B = scftb_engine_max_batch(g_bound);
+        for (int j0 = 0; j0 < n && batched; j0 += B) {
+          int nb = std::min(B, n - j0);
+          if (scftb_residual_ab_batch(g_bound, nb, &xb[(size_t)j0 * n], &fb[(size_t)j0 * n]) != SCFTB_OK) { scftb_funcerr = 1; }
         }
       }
       if (!batched)

@@ -45,6 +45,7 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_get_f0_given", "scftb_get_eta_full", "scftb_get_q_history", "scftb_free_energy",
            "scftb_bind_global", "scftb_callback_nr1", "scftb_callback_c0", "scftb_callback_fixedpoint_c0",
            "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_broydn_device", "scftb_broydn_device_ex", "scftb_adm_chen_batch",
+           "scftb_set_diblock", "scftb_residual_ab", "scftb_residual_ab_batch", "scftb_get_phi_ab", "scftb_callback_ab_c0",
            "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
            "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_refine_mesh_adaptive", "scftb_write_solution",
            "scftb_read_solution", "scftb_read_res", "scftb2d_nccl_unique_id", "scftb2d_create", "scftb2d_destroy",
@@ -72,7 +73,11 @@ def lib():
             getattr(L, nm).argtypes = [C.c_void_p, C.c_int, _dp]
         L.scftb_free_energy.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp]
         L.scftb_bind_global.argtypes = [C.c_void_p]
-        for nm in ("scftb_callback_nr1", "scftb_callback_c0", "scftb_callback_fixedpoint_c0"):
+        L.scftb_set_diblock.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        L.scftb_residual_ab.argtypes = [C.c_void_p, _dp, _dp]
+        L.scftb_residual_ab_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.scftb_get_phi_ab.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        for nm in ("scftb_callback_nr1", "scftb_callback_c0", "scftb_callback_fixedpoint_c0", "scftb_callback_ab_c0"):
             getattr(L, nm).restype = None
         L.scftb_adm_chen.argtypes = [C.c_void_p, _dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
         L.scftb_adm.argtypes = [C.c_void_p, _dp, C.c_int, _ip, C.c_int]
@@ -198,6 +203,25 @@ class Engine:
         F = C.c_double(0)
         _chk(lib().scftb_free_energy(self._h, p, f0bar, C.byref(F)))
         return F.value
+
+    # ---- two-species (AB diblock) extension: q and q+ as separate sweeps
+    def set_diblock(self, fA, chiN, p=-1):
+        _chk(lib().scftb_set_diblock(self._h, p, fA, chiN))
+
+    def residual_ab(self, w):
+        """w [2*ni] or [nprob, 2*ni] = (eta_A, eta_B) on the interior nodes -> residual of the same shape:
+        (sign*(phi0 - phiA - phiB), eta_A - eta_B - chiN*(phiB - phiA))"""
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        out = np.empty_like(w)
+        nprob = 1 if w.ndim == 1 else w.shape[0]
+        assert w.shape[-1] == 2 * self.ni
+        _chk(lib().scftb_residual_ab_batch(self._h, nprob, _p(w), _p(out)))
+        return out
+
+    def phi_ab(self, p=0):
+        a, b = np.empty(self.N), np.empty(self.N)
+        _chk(lib().scftb_get_phi_ab(self._h, p, _p(a), _p(b)))
+        return a, b
 
     def broydn_device(self, x0, tolf, jc=0, keep_trial=False):
         """scftb_broydn_device[_ex]: (rc, check, x, err, jc); keep_trial = SCFTB_BROYDN_KEEP_TRIAL"""
