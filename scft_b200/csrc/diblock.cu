@@ -152,7 +152,14 @@ int launch_ab(scftb_engine *e, DiblockState *s, int nprob, const double *d_w, do
     spline_bnd_launch(nprob, P.N, e->d_x, d_w + e->ni, P.eta_stride, s->d_scratch, s->d_eta_bndB, st);
   }
   const int grid = std::min(nprob, s->slots);
+  std::pair<cudaEvent_t, cudaEvent_t> ev;
+  if (e->timing) {   // same per-launch CUDA-event timing as the one-sweep march (scftb_set_timing / scftb_get_march_ms)
+    if (!e->ev_free.empty()) { ev = e->ev_free.back(); e->ev_free.pop_back(); }
+    else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
+    CK(cudaEventRecord(ev.first, st));
+  }
   s->kc.fn<<<grid, s->kc.T, 0, st>>>(P);
+  if (e->timing) { CK(cudaEventRecord(ev.second, st)); e->ev_pending.push_back(ev); }
   g_launches++;
   CK(cudaGetLastError());
   return SCFTB_OK;
