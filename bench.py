@@ -126,6 +126,22 @@ def oracle_throughput(count, threads):
     return count * (N_NODES - 2) * NSTEPS / dt, dt
 
 
+def reference_code_probe():
+    """One call of the reference's OWN spline_chen (dense gaussj on the (N-2)^2 spline matrix, spline_chen.c:23-68 called
+    from scft.cc:474 on every residual evaluation of the deal.II flow) at N=1025, compiled in place into oracle/_ref.
+    Informational: the step the unbuildable deal.II driver spends most of an m=1024 evaluation in."""
+    from oracle import oracle as O
+    if not O.have_ref():
+        return None
+    x = O.mesh_uniform(N_NODES)
+    eta = make_sweep(0, 1)[2][0]
+    t0 = time.perf_counter()
+    O.ref_spline(x[1:-1], eta, x)
+    dt = time.perf_counter() - t0
+    return {"what": "reference spline_chen + gaussj, one residual evaluation's field extension at N=1025, 1 thread",
+            "seconds": dt, "dof_steps_per_s_upper_bound": (N_NODES - 2) * NSTEPS / dt}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -310,6 +326,9 @@ def main():
             v, dt = oracle_throughput(cnt, cores)
             line["cpu_baseline"] = {"value": v, "unit": "DOF-steps/s", "cores": cores, "kind": "port",
                                     "sample": f"first {cnt} problems of the sweep, oracle/scft_oracle.c, {dt:.1f} s"}
+            probe = reference_code_probe()
+            if probe:
+                line["cpu_baseline"]["reference_code_probe"] = probe
         _emit(line)
     eng.close()
     if world > 1:
