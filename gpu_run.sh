@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q 2>&1 | tail -3
-python tools/lat.py 0 ab 2>&1 | tail -4 | tee gpurun_out/lat_ab.txt
-python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" 2>&1 | tail -2
-python bench.py > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err; cut -c1-300 gpurun_out/bench_r1_final.json
+ncu --set full --clock-control none --import-source on -k regex:march_ie -c 1 -f -o gpurun_out/prof_march_r1_final python tools/prof_march.py one > gpurun_out/ncu_one.log 2>&1; tail -2 gpurun_out/ncu_one.log
+ncu --set full --clock-control none --import-source on -k regex:march_ie -c 1 -f -o gpurun_out/prof_march_ab_r1 python tools/prof_march.py ab > gpurun_out/ncu_ab.log 2>&1; tail -2 gpurun_out/ncu_ab.log
+ls -la gpurun_out/*.ncu-rep
