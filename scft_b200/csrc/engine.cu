@@ -316,6 +316,11 @@ int scftb_destroy(scftb_engine *e) {
   for (double *p : {e->d_eta, e->d_out, e->d_phi, e->d_Q, e->d_f0, e->d_L, e->d_x, e->d_eta_bnd, e->d_w, e->d_hist,
                     e->d_eta_full, e->d_scratch})
     if (p) cudaFree(p);
+  for (cudaEvent_t ev : e->ev_pipe) cudaEventDestroy(ev);
+  for (auto &ev : e->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (auto &ev : e->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  if (e->s_in) cudaStreamDestroy(e->s_in);
+  if (e->s_out) cudaStreamDestroy(e->s_out);
   cudaStreamDestroy(e->stream);
   delete e;
   return SCFTB_OK;
@@ -347,18 +352,21 @@ int scftb_set_problem(scftb_engine *e, int p, double tau, double L, const double
 
 namespace scftb {
 int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_stride, double *d_out,
-                 long long out_stride, const int *d_skip, cudaStream_t st) {
+                 long long out_stride, const int *d_skip, cudaStream_t st, int p0) {
   MarchParams P{};
+  const size_t N = e->cfg.N, o = (size_t)p0;
   P.N = e->cfg.N; P.ni = e->ni; P.nsteps = e->cfg.nsteps;
   P.scheme = e->cfg.scheme; P.nprob = nprob; P.store_full = e->cfg.store_history;
   P.uniform = e->uniform ? 1 : 0; P.sign = e->cfg.sign;
   P.eta_mid = d_eta; P.eta_stride = eta_stride; P.out_stride = out_stride; P.skip = d_skip;
-  P.f0 = e->d_f0; P.L = e->d_L; P.x = e->d_x; P.eta_bnd = e->d_eta_bnd; P.w = e->d_w;
-  P.hist = e->d_hist; P.hist_stride = (long long)e->nslices * (long long)e->SL;
-  P.out = d_out; P.phi = e->d_phi; P.Q = e->d_Q; P.eta_full = e->d_eta_full;
+  P.f0 = e->d_f0 + o * N; P.L = e->d_L + o; P.w = e->d_w;
+  P.x = e->d_x ? e->d_x + o * N : nullptr; P.eta_bnd = e->d_eta_bnd ? e->d_eta_bnd + 2 * o : nullptr;
+  P.hist_stride = (long long)e->nslices * (long long)e->SL;
+  P.hist = e->d_hist + (e->cfg.store_history ? o * (size_t)P.hist_stride : 0);
+  P.out = d_out; P.phi = e->d_phi + o * N; P.Q = e->d_Q + o; P.eta_full = e->d_eta_full + o * N;
   if (!e->uniform) {
-    spline_bnd_kernel<<<(nprob + 63) / 64, 64, 0, st>>>(nprob, P.N, e->d_x, d_eta, eta_stride, e->d_scratch,
-                                                          e->d_eta_bnd);
+    spline_bnd_kernel<<<(nprob + 63) / 64, 64, 0, st>>>(nprob, P.N, P.x, d_eta, eta_stride, e->d_scratch + o * 2 * e->ni,
+                                                          e->d_eta_bnd + 2 * o);
     g_launches++;
   }
   int grid = std::min(nprob, e->slots);
@@ -396,12 +404,46 @@ int scftb_residual_batch(scftb_engine *e, int nprob, const double *eta_mid, doub
   CK(cudaSetDevice(e->cfg.device));
   int rc = upload_params(e);
   if (rc) return rc;
-  const size_t bytes = sizeof(double) * (size_t)e->ni * nprob;
-  CK(cudaMemcpyAsync(e->d_eta, eta_mid, bytes, cudaMemcpyHostToDevice, e->stream));
-  rc = launch_march(e, nprob, e->d_eta, e->ni, e->d_out, e->ni, nullptr, e->stream);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(out, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+  const size_t ni = e->ni;
+  const int waves = (nprob + e->slots - 1) / e->slots;
+  if (waves < 4) {   // small batch: one copy in, one launch, one copy out
+    const size_t bytes = sizeof(double) * ni * nprob;
+    CK(cudaMemcpyAsync(e->d_eta, eta_mid, bytes, cudaMemcpyHostToDevice, e->stream));
+    rc = launch_march(e, nprob, e->d_eta, e->ni, e->d_out, e->ni, nullptr, e->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SCFTB_OK;
+  }
+  // large batch: chunks of whole waves of resident CTAs; the copies of chunk c+1 / c-1 run on their own streams
+  // under the march of chunk c (pinned host buffers make them asynchronous; pageable ones still work)
+  const int chunk = e->slots * std::max(1, waves / 3);
+  const int nchunks = (nprob + chunk - 1) / chunk;
+  if (!e->s_in) {
+    CK(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+  }
+  while ((int)e->ev_pipe.size() < 2 * nchunks) {
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e->ev_pipe.push_back(ev);
+  }
+  CK(cudaStreamSynchronize(e->stream));   // parameters uploaded, earlier work on this engine finished
+  for (int c = 0; c < nchunks; c++) {
+    const int p0 = c * chunk, nb = std::min(chunk, nprob - p0);
+    const size_t off = ni * p0, bytes = sizeof(double) * ni * nb;
+    CK(cudaMemcpyAsync(e->d_eta + off, eta_mid + off, bytes, cudaMemcpyHostToDevice, e->s_in));
+    CK(cudaEventRecord(e->ev_pipe[2 * c], e->s_in));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_pipe[2 * c], 0));
+    rc = launch_march(e, nb, e->d_eta + off, e->ni, e->d_out + off, e->ni, nullptr, e->stream, p0);
+    if (rc) return rc;
+    CK(cudaEventRecord(e->ev_pipe[2 * c + 1], e->stream));
+    CK(cudaStreamWaitEvent(e->s_out, e->ev_pipe[2 * c + 1], 0));
+    CK(cudaMemcpyAsync(out + off, e->d_out + off, bytes, cudaMemcpyDeviceToHost, e->s_out));
+  }
+  CK(cudaStreamSynchronize(e->s_out));
   CK(cudaStreamSynchronize(e->stream));
+  e->last_nprob = nprob;
   return SCFTB_OK;
 }
 

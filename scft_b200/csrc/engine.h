@@ -56,6 +56,9 @@ struct scftb_engine {
   // optional per-launch timing of the march kernel (CUDA events on the launching stream)
   bool timing;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+  // copy streams + events of the pipelined host-buffer batch call (scftb_residual_batch), created on first use
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_pipe;
   // state a device-resident solver keeps between calls on this engine (Broyden's QR factors for jc), with its deleter
   void *solver_state = nullptr;
   void (*solver_state_free)(void *) = nullptr;
@@ -66,8 +69,9 @@ struct scftb_engine {
 
 namespace scftb {
 // launch one batch of residual evaluations; eta/out are device pointers with the given problem strides
+// p0: index of the first problem of this launch in the engine's per-problem arrays (d_eta / d_out already point at it)
 int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_stride, double *d_out,
-                 long long out_stride, const int *d_skip, cudaStream_t st);
+                 long long out_stride, const int *d_skip, cudaStream_t st, int p0 = 0);
 int upload_params(scftb_engine *e);
 }  // namespace scftb
 

@@ -96,3 +96,41 @@ def test_odd_number_of_steps_with_trapezoid(sb, oracle, fixtures):
             ref = oracle.residual(oracle.eta_full(x, em), oracle.f0_given(x), scheme=scheme, nsteps=n, quadrature=1)
             assert np.abs(eng.phi() - ref["phi"]).max() < 1e-10 * np.abs(ref["phi"]).max()
             eng.close()
+
+
+def test_large_host_batch_goes_through_the_chunked_copy_pipeline(sb, oracle):
+    """scftb_residual_batch splits batches of >= 4 waves of resident CTAs into chunks whose copies overlap the march:
+    every chunk must use its own problems' parameters (tau, L), outputs and history"""
+    N, n, B = 33, 32, 12000
+    rng = np.random.default_rng(77)
+    eng = sb.Engine(N, nsteps=n, scheme=0, max_batch=B, store_history=True)
+    taus, Ls = rng.uniform(0.40, 0.66, B), rng.uniform(3.2, 4.2, B)
+    for p in range(B):
+        eng.set_problem(p, taus[p], Ls[p])
+    eta = rng.standard_normal((B, N - 2))
+    out = eng.residual(eta)
+    for p in (0, 1, 2999, 3000, 5999, 6001, 9000, 11999):
+        x = oracle.mesh_uniform(N, Ls[p])
+        ref = oracle.residual(oracle.eta_full(x, eta[p]), oracle.f0_given(x, taus[p]), scheme=0, nsteps=n, L=Ls[p],
+                              want_hist=True)
+        assert np.abs(out[p] - ref["out"]).max() < 1e-12
+        assert np.abs(eng.phi(p) - ref["phi"]).max() < 1e-12
+        assert abs(eng.Q(p) - ref["Q"]) < 1e-12
+        assert np.abs(eng.q_history(p) - ref["hist"]).max() < 1e-12
+    eng.close()
+
+
+def test_large_host_batch_on_a_nonuniform_mesh(sb, oracle, fixtures):
+    x = fixtures["matlab43_x"]
+    N, n, B = len(x), 16, 8000
+    L = x[-1] - x[0]
+    rng = np.random.default_rng(78)
+    eng = sb.Engine(N, nsteps=n, scheme=1, max_batch=B, tau=0.5302, L=L, x=x)
+    eta = rng.standard_normal((B, N - 2))
+    out = eng.residual(eta)
+    f0 = oracle.f0_given(x, 0.5302)
+    for p in (0, 2500, 5000, 7999):
+        ref = oracle.residual(oracle.eta_full(x, eta[p]), f0, scheme=1, nsteps=n, L=L, x=x)
+        assert np.abs(out[p] - ref["out"]).max() < 1e-12
+        assert np.abs(eng.eta_full(p) - oracle.eta_full(x, eta[p])).max() < 1e-12
+    eng.close()
