@@ -37,7 +37,8 @@ __device__ __forceinline__ cx rfma(cx a, double x, cx c) { return mk(fma(a.re, x
 __device__ __forceinline__ cx shfl_up_c(cx v, int d) { return mk(shfl_up_d(v.re, d), shfl_up_d(v.im, d)); }
 __device__ __forceinline__ cx shfl_dn_c(cx v, int d) { return mk(shfl_dn_d(v.re, d), shfl_dn_d(v.im, d)); }
 
-constexpr int PUBC = 12;  // doubles per warp: [0] qf, [2,3] zf, [4,5] Z0 (lane 0); [6,7] Z30 (lane 30); [8,9] rsep (lane 31)
+constexpr int PUBC = 18;  // doubles per warp: [0] qf, [2,3] zf, [4,5] Z0 (lane 0); [6,7] Z30 (lane 30); [8,9] rsep (lane 31); 144-byte rows keep the
+                          // level-3 loads of up to eight rows in disjoint banks (96-byte rows conflicted 2-way)
 
 template <int C, int T, bool UNI>
 __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
