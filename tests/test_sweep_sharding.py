@@ -69,3 +69,19 @@ def test_two_rank_gloo_sweep_equals_single_process(total):
     ref = _fake_eval(0, total)
     for r in range(2):
         assert np.array_equal(got[r], ref)
+
+
+def test_continuation_level_ladder_is_checked_before_any_engine_is_created():
+    """33 -> 65 -> ... by bisection only: an unreachable target is an argument error (no GPU needed to say so)"""
+    import pytest
+    from scft_b200 import sweep
+    with pytest.raises(ValueError, match="not reachable"):
+        sweep.Continuation(N_target=1000, N0=33)
+
+
+def test_sweep_params_cover_the_tau_L_grid():
+    from scft_b200 import sweep
+    cells = {sweep.sweep_params(p)[:2] for p in range(256)}
+    assert len(cells) == 256                                  # 16 x 16 distinct (tau, L) cells
+    assert sweep.sweep_params(0)[:2] == sweep.sweep_params(256)[:2]   # then the seed axis
+    assert sweep.sweep_params(0)[2] != sweep.sweep_params(256)[2]
