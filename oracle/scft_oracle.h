@@ -15,9 +15,10 @@
  *       DEALII_SCFT/inputFiles/N=33_for_read.txt (residual <= 2e-9, F to 1e-15)
  *   romint / spline / gaussj / adm / adm_chen / broydn : pinned against the
  *       reference's own C compiled into oracle/_ref (tests/test_oracle_vs_ref.py)
- *   IE_ROWSCALE, IE_CONSISTENT, Q : PARITY UNPINNED by any reference artefact
- *       (1D_FEM.c needs PETSc and records no output); the restatement of
- *       Matlab_files/simple_FEM_1D_transient.m is the only oracle.
+ *   IE_ROWSCALE : pinned by Matlab_files/inputFiles/solution_matlab_N=33, a converged solution of
+ *       Matlab_files/simple_FEM_1D_transient.m (2049 steps of dt = 1/2048, trapezoid): residual 2.3e-7 at the
+ *       MATLAB run's tolerance 1e-7 (tests/test_oracle_golden.py; 1D_FEM.c itself needs PETSc and records no output)
+ *   IE_CONSISTENT, Q, two-species : PARITY UNPINNED by any reference artefact (oracle only)
  */
 #ifndef SCFT_ORACLE_H_
 #define SCFT_ORACLE_H_

@@ -55,6 +55,11 @@ def main():
         s = O.read_yita_file(f"{REF}/Matlab_files/inputFiles/solution_yita_1D_N= {n}.txt")
         fx[f"matlab{n}_x"] = s["x"]
         fx[f"matlab{n}_eta"] = s["eta"]
+    # a converged solution of Matlab_files/simple_FEM_1D_transient.m (drive_SCFT.m: tau=0.5302, L=3.72374, adm_chen to 1e-7):
+    # the one reference artefact that pins the implicit-Euler / row-scaled scheme
+    s = O.read_yita_file(f"{REF}/Matlab_files/inputFiles/solution_matlab_N=33")
+    fx["matlab33_x"] = s["x"]
+    fx["matlab33_eta"] = s["eta"]
     np.savez_compressed(os.path.join(OUT, "ref_fixtures.npz"), **fx)
 
     out = {}

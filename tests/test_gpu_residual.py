@@ -122,3 +122,21 @@ def test_free_energy_matches_fixture(sb, oracle, fixtures):
     assert eng.free_energy() == pytest.approx(float(fixtures["n33_F"]), abs=1e-15)
     assert eng.free_energy(f0bar=0.0) == pytest.approx(float(fixtures["n33_F"]), abs=1e-14)
     eng.close()
+
+
+def test_matlab_converged_solution_is_a_fixed_point_on_the_gpu(sb, oracle, fixtures):
+    """Reference artefact for the implicit-Euler / row-scaled scheme: Matlab_files/inputFiles/solution_matlab_N=33, a
+    converged solution of simple_FEM_1D_transient.m (2049 steps of dt = 1/2048, trapezoid rule, tau = 0.5302,
+    L = 3.72374).  The similarity x -> c x, tau -> c tau, eta -> eta*2049/2048, phi -> phi*2049/2048 with
+    c = sqrt(2048/2049) maps that march onto nsteps = 2049 of the engine (tests/test_oracle_golden.py)."""
+    x, eta = fixtures["matlab33_x"], fixtures["matlab33_eta"]
+    tau, L, c, s = 0.5302, 3.72374, np.sqrt(2048.0 / 2049.0), 2049.0 / 2048.0
+    eng = sb.Engine(33, nsteps=2049, scheme=0, quadrature=sb.QUAD_TRAPEZOID, tau=tau * c, L=L * c)
+    eng.residual(eta[1:-1] * s)
+    phi = eng.phi()
+    f0 = oracle.f0_given(x, tau)
+    ref = oracle.residual(eta * s, f0, scheme=0, nsteps=2049, L=L * c, quadrature=1)
+    assert np.abs(phi - ref["phi"]).max() < 1e-10 * np.abs(ref["phi"]).max()
+    assert np.abs(eng.f0_given() - f0).max() < 1e-12
+    assert np.abs(f0[1:-1] - phi[1:-1] * s).max() < 3e-7      # converged to the MATLAB run's 1e-7 (2.33e-7)
+    eng.close()

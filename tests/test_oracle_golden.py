@@ -180,3 +180,57 @@ def test_strip_mesh_reduces_to_1d(oracle, fixtures):
     top = hist[1::2]
     assert np.abs(bottom - top).max() < 1e-12               # y-invariant
     assert np.abs(bottom - r["hist"][1:-1]).max() < 1e-11   # equals the 1D restatement
+
+
+# ---- the reference artefact that pins the implicit-Euler / row-scaled scheme -------------------------------------
+# Matlab_files/inputFiles/solution_matlab_N=33 is a converged solution of Matlab_files/simple_FEM_1D_transient.m
+# (drive_SCFT.m:4-18: tau = 0.5302, L = 3.72374, adm_chen to 1e-7).  That function marches time_step = 2049 steps of
+# dt = 1/2048 (:17-18,:85-117: the prototype's 2049-vs-2048 defect) and integrates with the trapezoid rule (:120-127).
+# The engine/oracle use ds = 1/nsteps; the MATLAB march is reproduced EXACTLY with nsteps = 2049 by the similarity
+#   x -> c x, tau -> c tau, eta -> eta * 2049/2048, phi -> phi * 2049/2048,  c = sqrt(2048/2049)
+# (A + ds(B + eta A) scales by c when ds/c^2 and ds*eta are kept; phi_0 depends on x/tau only).
+MATLAB_TAU, MATLAB_L = 0.5302, 3.72374
+
+
+def matlab_scaled_problem(fixtures):
+    x, eta = fixtures["matlab33_x"], fixtures["matlab33_eta"]
+    c = np.sqrt(2048.0 / 2049.0)
+    return x, eta, c
+
+
+def test_ie_rowscale_pinned_by_the_matlab_converged_solution(oracle, fixtures):
+    x, eta, c = matlab_scaled_problem(fixtures)
+    xs = oracle.mesh_uniform(33, MATLAB_L * c)
+    f0 = oracle.f0_given(x, MATLAB_TAU)
+    assert np.abs(oracle.f0_given(xs, MATLAB_TAU * c) - f0).max() < 1e-15
+    res = oracle.residual(eta * 2049.0 / 2048.0, f0, scheme=oracle.IE_ROWSCALE, nsteps=2049, L=MATLAB_L * c,
+                          quadrature=oracle.QUAD_TRAPEZOID)
+    out = f0[1:-1] - res["phi"][1:-1] * 2049.0 / 2048.0
+    assert np.abs(out).max() < 3e-7           # the file is converged to adm_chen's 1e-7 (measured 2.33e-7)
+
+
+def test_oracle_equals_a_dense_restatement_of_the_matlab_function(oracle, fixtures):
+    """simple_FEM_1D_transient.m:34-128 restated with dense numpy matrices (inv(D) as the .m file does)"""
+    x, eta, c = matlab_scaled_problem(fixtures)
+    N, ni, dt = len(x), len(x) - 2, 1.0 / 2048
+    a1, a2 = np.diff(x)[:-1], np.diff(x)[1:]
+    A, B = np.zeros((ni, ni)), np.zeros((ni, ni))
+    for i in range(ni):                                                    # :35-63 (interior rows)
+        A[i, i], B[i, i] = a1[i] / 3 + a2[i] / 3, 1 / a1[i] + 1 / a2[i]
+        if i > 0:
+            A[i, i - 1], B[i, i - 1] = a1[i] / 6, -1 / a1[i]
+        if i < ni - 1:
+            A[i, i + 1], B[i, i + 1] = a2[i] / 6, -1 / a2[i]
+    Dinv = np.linalg.inv(A + dt * (B + np.diag(eta[1:-1]) @ A))            # :66-80
+    q, H = np.ones(ni), [np.ones(ni)]
+    for _ in range(2049):                                                  # :85-117, time_step = 2049
+        q = Dinv @ (A @ q)
+        H.append(q.copy())
+    H = np.array(H)
+    v = H * H[::-1]
+    phi = dt * (v[0] / 2 + v[1:-1].sum(axis=0) + v[-1] / 2)                # :120-127
+    f0 = oracle.f0_given(x, MATLAB_TAU)
+    res = oracle.residual(eta * 2049.0 / 2048.0, f0, scheme=oracle.IE_ROWSCALE, nsteps=2049, L=MATLAB_L * c,
+                          quadrature=oracle.QUAD_TRAPEZOID)
+    assert np.abs(res["phi"][1:-1] * 2049.0 / 2048.0 - phi).max() < 1e-12
+    assert np.abs(f0[1:-1] - phi).max() < 3e-7
