@@ -51,8 +51,11 @@ def main():
         fx[f"res{m}_eta"] = r["eta"]
         for k, v in r["meta"].items():
             fx[f"res{m}_{k}"] = v
-    for n in (43, 59):
+    for n in (33, 43, 59):   # key matlab33s_*: "solution_yita_1D_N= 33.txt" (matlab33_* is solution_matlab_N=33)
         s = O.read_yita_file(f"{REF}/Matlab_files/inputFiles/solution_yita_1D_N= {n}.txt")
+        if n == 33:
+            fx["matlab33s_x"], fx["matlab33s_eta"] = s["x"], s["eta"]
+            continue
         fx[f"matlab{n}_x"] = s["x"]
         fx[f"matlab{n}_eta"] = s["eta"]
     # a converged solution of Matlab_files/simple_FEM_1D_transient.m (drive_SCFT.m: tau=0.5302, L=3.72374, adm_chen to 1e-7):

@@ -111,3 +111,12 @@ def test_adaptive_refinement_follows_matlab_prototype(sb, oracle, fixtures):
         xm = fixtures[f"matlab{n_nodes}_x"]
         h = np.diff(xm)
         assert h[:3].max() < h[len(h) // 2]
+
+
+def test_adaptive_refinement_reproduces_the_prototypes_own_mesh(sb, fixtures):
+    """reference artefact: Matlab_files/refine_mesh.m applied to the field of 'solution_yita_1D_N= 33.txt' produced the
+    43-node mesh stored in 'solution_yita_1D_N= 43.txt' — scftb_refine_mesh_adaptive gives the same nodes"""
+    x, eta = fixtures["matlab33s_x"], fixtures["matlab33s_eta"]
+    xn, en = sb.refine_mesh_adaptive(x, eta[1:-1])
+    assert len(xn) == 43 and np.abs(xn - fixtures["matlab43_x"]).max() < 1e-12
+    assert len(en) == 41 and np.all(np.isfinite(en))
