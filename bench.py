@@ -6,8 +6,9 @@ SCFT problems over (tau, L, perturbed eta0), m=1024 elements (N=1025 nodes, 1023
 n=2048 implicit-Euler contour steps, P=1 propagator sweep per evaluation (the reference's
 symmetric one-sweep form q+(x,s)=q(x,1-s), drivescft.cc:189-190).  One "step" is one SCFT
 iteration of every problem of the batch: a residual evaluation (the march kernel) followed by
-the field update.  Problems are sharded across ranks with no data-path collective (weak scaling:
-4096 problems per GPU).
+the field update.  The 4096 problems of the sweep are sharded across the ranks in contiguous blocks with no
+data-path collective: STRONG scaling (4096 / N problems per GPU), as BASELINE.json words configs[2].  At N > 1 a
+second, weak-scaling leg (4096 problems per GPU) is reported under the extra key "weak".
 
     python bench.py --gpus N --steps K --warmup W            # our arm
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
@@ -30,7 +31,7 @@ sys.path.insert(0, ROOT)
 N_NODES = 1025
 NSTEPS = 2048
 SCHEME = 0  # IE, row-scaled C: the scheme of 1D_FEM.c:95-186
-PROBLEMS_PER_GPU = 4096
+TOTAL_PROBLEMS = 4096   # the sweep of BASELINE.json configs[2]; sharded over the ranks
 BYTES_PER_DOF_STEP = 8.0  # lean history: each q(x_i,s_j), j<n/2, is written once and read once => 4+4 B per DOF-step
 
 
@@ -102,64 +103,88 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def oracle_throughput(count, threads):
-    """DOF-steps/s of the CPU oracle (the reference algorithm restated in C) on `count` problems
-    of the same sweep, `threads` host threads (ctypes releases the GIL)."""
+def fair_cpu_throughput(first, count, threads):
+    """DOF-steps/s of the fair CPU port (oracle/scft_fast.c: Thomas once per field, half history, 8 problems per SIMD
+    group, `threads` POSIX threads) on problems [first, first+count) of the sweep."""
+    from oracle import oracle as O
+    O.lib()
+    taus, Ls, eta = make_sweep(first, count)
+    t0 = time.perf_counter()
+    r = O.fast_sweep(taus, Ls, eta, N_NODES, scheme=SCHEME, nsteps=NSTEPS, threads=threads, want_phi=False)
+    dt = time.perf_counter() - t0
+    assert np.isfinite(r["out"]).all()
+    return count * (N_NODES - 2) * NSTEPS / dt, dt
+
+
+def checker_throughput(count, threads):
+    """DOF-steps/s of the checker oracle (oracle/scft_oracle.c: pivoting band LU, full history) — round 1's CPU arm"""
     from oracle import oracle as O
     O.lib()
     taus, Ls, eta = make_sweep(0, count)
 
     def one(i):
         x = O.mesh_uniform(N_NODES, Ls[i])
-        f0 = O.f0_given(x, taus[i])
-        ef = O.eta_full(x, eta[i])
-        return O.residual(ef, f0, scheme=SCHEME, nsteps=NSTEPS, L=Ls[i])["Q"]
+        return O.residual(O.eta_full(x, eta[i]), O.f0_given(x, taus[i]), scheme=SCHEME, nsteps=NSTEPS, L=Ls[i])["Q"]
 
     t0 = time.perf_counter()
-    if threads == 1:
-        for i in range(count):
-            one(i)
-    else:
-        with ThreadPoolExecutor(threads) as ex:
-            list(ex.map(one, range(count)))
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(one, range(count)))
     dt = time.perf_counter() - t0
     return count * (N_NODES - 2) * NSTEPS / dt, dt
 
 
-def reference_code_probe():
-    """One call of the reference's OWN spline_chen (dense gaussj on the (N-2)^2 spline matrix, spline_chen.c:23-68 called
-    from scft.cc:474 on every residual evaluation of the deal.II flow) at N=1025, compiled in place into oracle/_ref.
-    Informational: the step the unbuildable deal.II driver spends most of an m=1024 evaluation in."""
+def reference_faithful_leg(evals=3):
+    """The reference CPU path as the reference runs it (SURVEY.md 8d "reference-faithful, 1 thread"):
+    ONE host thread, the reference's own adm_chen (ADM_chen_C.c, compiled in place into oracle/_ref) driving a residual
+    whose field extension is the reference's own spline_chen + dense gaussj (spline_chen.c:23-68 from scft.cc:474,
+    O(N^3) per evaluation) followed by the oracle's IRK4 march and romint quadrature (deal.II / UMFPACK themselves are
+    unbuildable here).  m = 1024: a few evaluations only, stated."""
     from oracle import oracle as O
     if not O.have_ref():
         return None
     x = O.mesh_uniform(N_NODES)
-    eta = make_sweep(0, 1)[2][0]
+    f0 = O.f0_given(x)
+    eta0 = make_sweep(0, 1)[2][0]
+    calls = []
+
+    def F(em):
+        t0 = time.perf_counter()
+        ef = O.ref_spline(x[1:-1], em, x)
+        t1 = time.perf_counter()
+        out = O.residual(ef, f0, scheme=O.IRK4_CONSISTENT, nsteps=NSTEPS)["out"]
+        calls.append((t1 - t0, time.perf_counter() - t1))
+        return out
+
     t0 = time.perf_counter()
-    O.ref_spline(x[1:-1], eta, x)
+    O.ref_adm_chen(F, eta0, 1e-30, evals - 1, 0.99, 2)
     dt = time.perf_counter() - t0
-    return {"what": "reference spline_chen + gaussj, one residual evaluation's field extension at N=1025, 1 thread",
-            "seconds": dt, "dof_steps_per_s_upper_bound": (N_NODES - 2) * NSTEPS / dt}
+    n = len(calls)
+    return {"what": "reference adm_chen (oracle/_ref) driving reference spline_chen+gaussj + oracle IRK4 march + romint, "
+                    "m=1024 n=2048, 1 host thread", "evaluations": n, "seconds": dt,
+            "seconds_per_evaluation": dt / n, "spline_gaussj_seconds_per_evaluation": sum(c[0] for c in calls) / n,
+            "march_seconds_per_evaluation": sum(c[1] for c in calls) / n,
+            "value": n * (N_NODES - 2) * NSTEPS / dt, "unit": "DOF-steps/s", "cores": 1}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     cores = host_cores()
-    per_step = max(cores, 8) * 16
+    per_step = 512                      # one eighth of the sweep per step: a fraction of a second on 16 threads
     for _ in range(args.warmup):
-        oracle_throughput(max(cores, 8), cores)
+        fair_cpu_throughput(0, 64, cores)
     t = []
-    for _ in range(args.steps):
-        v, dt = oracle_throughput(per_step, cores)
+    for k in range(args.steps):
+        v, dt = fair_cpu_throughput((k * per_step) % TOTAL_PROBLEMS, per_step, cores)
         t.append(dt)
     tot = sum(t)
     value = args.steps * per_step * (N_NODES - 2) * NSTEPS / tot
-    sample = f"{per_step} problems of the sweep per step (of {PROBLEMS_PER_GPU} per GPU), {cores} host threads"
+    sample = (f"{per_step} problems of the 4096-problem sweep per step, fair CPU port oracle/scft_fast.c "
+              f"(Thomas once per field, half history, AVX SIMD over 8 problems), {cores} host threads")
     line = {"impl": "reference", "metric": "propagator_dof_steps_per_s", "value": value, "unit": "DOF-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(per_step),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(-(-TOTAL_PROBLEMS // max(args.gpus, 1)), max(args.gpus, 1)),
             "scft_residual_evaluations_per_s": args.steps * per_step / tot,
             "cpu_baseline": {"value": value, "unit": "DOF-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "DOF-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -167,15 +192,90 @@ def run_reference(args, rank):
     _emit(line)
 
 
-def workload_config(problems_per_gpu):
-    return {"workload": "sweep of independent 1D hard-surface SCFT problems (tau x L x eta0-seed grid), "
+def workload_config(problems_per_gpu, world, total=TOTAL_PROBLEMS):
+    return {"workload": "sweep of 4096 independent 1D hard-surface SCFT problems (tau x L x eta0-seed grid), "
                         "m=1024 n=2048 implicit Euler (BASELINE.json configs[2])",
-            "problems_per_gpu": problems_per_gpu, "N": N_NODES, "unknowns": N_NODES - 2, "nsteps": NSTEPS,
-            "scheme": "IE_ROWSCALE (1D_FEM.c:95-186)", "propagator_sweeps_P": 1,
+            "problems_total": total, "problems_per_gpu": problems_per_gpu, "N": N_NODES, "unknowns": N_NODES - 2,
+            "nsteps": NSTEPS, "scheme": "IE_ROWSCALE (1D_FEM.c:95-186)", "propagator_sweeps_P": 1,
             "step": "one SCFT iteration of every problem: residual evaluation + Anderson field update",
             "skipped_problems": 0,
-            "l2": "inputs larger than L2: each step streams the q history (>3 GB per GPU) through HBM",
-            "parallelism": "problems sharded by rank, no data-path collective"}
+            "l2": "inputs larger than L2: each step streams the q history (> 0.5 GB per GPU even at N=8) through HBM",
+            "parallelism": f"4096 problems sharded over {world} rank(s) in contiguous blocks, no data-path collective"}
+
+
+class SweepRun:
+    """problems [p0, p1) of the sweep resident on this rank's GPU: engine + device-resident Anderson mixer"""
+
+    def __init__(self, p0, p1, local, torch, scft_b200):
+        self.P = p1 - p0
+        self.taus, self.Ls, self.eta = make_sweep(p0, self.P)
+        self.eng = scft_b200.Engine(N_NODES, nsteps=NSTEPS, scheme=SCHEME, max_batch=self.P, device=local)
+        for p in range(self.P):
+            self.eng.set_problem(p, self.taus[p], self.Ls[p])
+        dev = torch.device("cuda", local)
+        self.h_eta = torch.from_numpy(self.eta).pin_memory()
+        self.h_out = torch.empty_like(self.h_eta).pin_memory()
+        self.d_eta = self.h_eta.to(dev, non_blocking=True)
+        self.stream = torch.cuda.current_stream()
+        # relaxation of the reference's first Anderson stage (adm_chen(..., 0.99, 2), drivescft.cc:294) with a window of
+        # ONE: from the perturbed spectral guess the two-vector extrapolation overshoots on ~1 % of the 4096 problems
+        # (residuals overflow after ~10 iterations, tools/mixer_stability.py), the one-vector window keeps every problem
+        # finite and descending.  tol unreachable and freeze off, so EVERY problem is evaluated in EVERY step.
+        self.mixer = scft_b200.AndersonBatch(self.eng, self.P, tol=1e-30, lmd=0.99, nn=1)
+        self.mixer.set_freeze(False)
+        self.mixer.reset_device(self.d_eta.data_ptr(), self.stream.cuda_stream)
+
+    def step(self):
+        """one SCFT iteration of the resident problems, fields resident in HBM"""
+        self.mixer.iterate_device(self.stream.cuda_stream)
+
+    def reset(self):
+        self.mixer.reset_device(self.d_eta.data_ptr(), self.stream.cuda_stream)
+
+    def close(self):
+        self.mixer.close()
+        self.eng.close()
+
+
+def timed_steps(run, steps, warmup, barrier, torch):
+    """(ms for `steps` steps on this rank, mean march-kernel ms, launches): CUDA events on the launching stream"""
+    import scft_b200
+    for _ in range(warmup):
+        run.step()
+    run.reset()                       # timed iterations start from the sweep's own fields
+    run.eng.set_timing(True)
+    barrier()
+    scft_b200.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    run.eng.march_ms()                # drop earlier launches
+    ev0.record(run.stream)
+    for _ in range(steps):
+        run.step()
+    ev1.record(run.stream)
+    barrier()
+    launches = scft_b200.launch_count()
+    tot, cnt = run.eng.march_ms()
+    run.eng.set_timing(False)
+    return ev0.elapsed_time(ev1), tot / max(cnt, 1), launches
+
+
+def parity_spot_check(run, count=8):
+    """`count` problems of this rank's shard against the CPU oracle (checker): phi, Q, residual of the fields the e2e
+    leg just evaluated through scftb_residual_batch.  Returns (checked, max relative error)."""
+    from oracle import oracle as O
+    O.lib()
+    P = run.P
+    slots = run.eng.slots()
+    pts = sorted({0, P - 1, P // 2, min(P - 1, slots - 1), min(P - 1, slots), min(P - 1, 2 * slots), P // 3, (2 * P) // 3})[:count]
+    out = run.h_out.numpy()
+    worst = 0.0
+    for p in pts:
+        x = O.mesh_uniform(N_NODES, run.Ls[p])
+        ref = O.residual(O.eta_full(x, run.eta[p]), O.f0_given(x, run.taus[p]), scheme=SCHEME, nsteps=NSTEPS, L=run.Ls[p])
+        scale = np.abs(ref["phi"]).max()
+        worst = max(worst, np.abs(run.eng.phi(p) - ref["phi"]).max() / scale, abs(run.eng.Q(p) - ref["Q"]) / abs(ref["Q"]),
+                    np.abs(out[p] - ref["out"]).max() / scale)
+    return len(pts), float(worst)
 
 
 def main():
@@ -189,8 +289,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--problems", type=int, default=PROBLEMS_PER_GPU, help="problems per GPU")
+    ap.add_argument("--problems", type=int, default=TOTAL_PROBLEMS, help="problems of the whole sweep (sharded over the ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling leg at N > 1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,34 +304,17 @@ def main():
     import torch
     import torch.distributed as dist
     import scft_b200
+    from scft_b200 import sweep
 
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    P = args.problems
+    total = args.problems
     ni = N_NODES - 2
-
-    taus, Ls, eta = make_sweep(rank * P, P)
-    eng = scft_b200.Engine(N_NODES, nsteps=NSTEPS, scheme=SCHEME, max_batch=P, device=local)
-    for p in range(P):
-        eng.set_problem(p, taus[p], Ls[p])
-    h_eta = torch.from_numpy(eta).pin_memory()
-    h_out = torch.empty_like(h_eta).pin_memory()
-    d_eta = h_eta.to(dev, non_blocking=True)
-    d_out = torch.empty_like(d_eta)
-    stream = torch.cuda.current_stream()
-    # fixed-iteration benchmark: tol unreachable and freeze off, so EVERY problem is evaluated in EVERY step
-    # (Anderson from the perturbed spectral guess diverges for a few percent of the problems; the reference
-    # would exit(1) on their NaNs — here they keep costing the full march)
-    mixer = scft_b200.AndersonBatch(eng, P, tol=1e-30, lmd=0.99, nn=2)
-    mixer.set_freeze(False)
-    mixer.reset_device(d_eta.data_ptr(), stream.cuda_stream)
-    eng.set_timing(True)
-
-    def step():
-        """one SCFT iteration of the batch, fields resident in HBM"""
-        mixer.iterate_device(stream.cuda_stream)
+    p0, p1 = sweep.shard(total, rank, world)
+    run = SweepRun(p0, p1, local, torch, scft_b200)
+    P = run.P
 
     def barrier():
         torch.cuda.synchronize()
@@ -238,99 +322,117 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    # ---- device-resident timing (strong scaling: this rank's block of the 4096-problem sweep)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        step()
-    mixer.reset_device(d_eta.data_ptr(), stream.cuda_stream)   # timed iterations start from the sweep's fields
     barrier()
-    scft_b200.launch_count(reset=True)
     t_begin = time.time()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.march_ms()  # drop the warm-up launches
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step()
-    ev1.record(stream)
-    barrier()
+    ms, march_ms, launches = timed_steps(run, args.steps, args.warmup, barrier, torch)
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
-    launches = scft_b200.launch_count()
-    ms = ev0.elapsed_time(ev1)
-    march_tot, march_cnt = eng.march_ms()
-    eng.set_timing(False)
-    t = torch.tensor([ms, march_tot / max(march_cnt, 1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, march_ms_avg = float(t[0]), float(t[1])
+    ms_total, march_ms_avg = max_over_ranks([ms, march_ms])
+    done, iters, err = run.mixer.status(run.stream.cuda_stream)
+    finite_local = float(np.isfinite(err).sum())
 
     # ---- end to end through the C ABI with host buffers (H2D + kernel + D2H inside the call)
     barrier()
     for _ in range(2):
-        eng.residual_host_ptr(P, h_eta.data_ptr(), h_out.data_ptr())
+        run.eng.residual_host_ptr(P, run.h_eta.data_ptr(), run.h_out.data_ptr())
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.residual_host_ptr(P, h_eta.data_ptr(), h_out.data_ptr())
+        run.eng.residual_host_ptr(P, run.h_eta.data_ptr(), run.h_out.data_ptr())
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te[0])
+    e2e_s = max_over_ranks([time.perf_counter() - t0])[0]
+
+    # ---- parity: a handful of this rank's problems against the CPU oracle (rank 0 reports; every rank checks)
+    checked, max_rel = parity_spot_check(run)
+    max_rel_all = max_over_ranks([max_rel])[0]
 
     # per-problem scalars of the whole sweep: the one collective of the workload, outside the timed region
-    from scft_b200 import sweep
-    done, iters, err = mixer.status(stream.cuda_stream)
-    local = np.stack([err, iters.astype(np.float64)], axis=1)
-    allres = sweep.gather_results(local, world * P, rank, world) if world > 1 else local
+    local_rows = np.stack([err, iters.astype(np.float64)], axis=1)
+    allres = sweep.gather_results(local_rows, total, rank, world) if world > 1 else local_rows
+    run.close()
+
+    # ---- extra: weak scaling (4096 problems on every GPU), N > 1 only
+    weak = None
+    if world > 1 and not args.no_weak:
+        wrun = SweepRun(rank * TOTAL_PROBLEMS, (rank + 1) * TOTAL_PROBLEMS, local, torch, scft_b200)
+        wms, wmarch, _ = timed_steps(wrun, args.steps, args.warmup, barrier, torch)
+        wms, wmarch = max_over_ranks([wms, wmarch])
+        wrun.close()
+        weak = {"scaling": "weak", "problems_per_gpu": TOTAL_PROBLEMS,
+                "value": world * TOTAL_PROBLEMS * ni * NSTEPS * args.steps / (wms * 1e-3), "unit": "DOF-steps/s",
+                "ms_per_step": wms / args.steps, "march_kernel_ms": wmarch,
+                "hbm_frac_per_gpu": TOTAL_PROBLEMS * ni * NSTEPS * BYTES_PER_DOF_STEP / (wmarch * 1e-3) / 1e9}
+
     if rank == 0:
-        assert allres.shape[0] == world * P
+        assert allres.shape[0] == total
         finite = int(np.isfinite(allres[:, 0]).sum())
-        dof_steps_per_step = world * P * ni * NSTEPS
+        dof_steps_per_step = total * ni * NSTEPS
         value = dof_steps_per_step * args.steps / (ms_total * 1e-3)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        algo_bytes = P * ni * NSTEPS * BYTES_PER_DOF_STEP
+        if weak:
+            weak["hbm_frac_per_gpu"] /= peak
+        Pmax = -(-total // world)   # the largest block: the rank whose kernel time is reported
+        algo_bytes = Pmax * ni * NSTEPS * BYTES_PER_DOF_STEP
         traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one march launch (ncu --set full capture)
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):
-            tr = json.load(open(tpath))["march_ie_kernel"]
-            if tr["problems"] == P and tr["N"] == N_NODES and tr["nsteps"] == NSTEPS:
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        for name in ("r2_traffic.json", "r1_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath):
+                tr = json.load(open(tpath))["march_ie_kernel"]
+                if tr["N"] == N_NODES and tr["nsteps"] == NSTEPS:   # per-launch traffic scales with the problem count
+                    traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * Pmax / tr["problems"]
+                    break
         achieved = algo_bytes / (march_ms_avg * 1e-3) / 1e9
         line = {"metric": "propagator_dof_steps_per_s", "value": value, "unit": "DOF-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(P),
-                "scft_iterations_per_s": world * P * args.steps / (ms_total * 1e-3),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(Pmax, world, total),
+                "scft_iterations_per_s": total * args.steps / (ms_total * 1e-3),
                 "problems_with_finite_residual_at_end": finite,
+                "parity_checked": checked * world, "max_rel_err": max_rel_all,
+                "parity": "phi, Q, residual of sampled problems vs the CPU oracle (oracle/scft_oracle.c), tolerance 1e-10",
                 "clocks": clocks,
                 "e2e": {"value": dof_steps_per_step * args.steps / e2e_s, "unit": "DOF-steps/s",
                         "h2d_bytes_per_step": P * ni * 8, "d2h_bytes_per_step": P * ni * 8,
-                        "call": "scftb_residual_batch (pinned host buffers), wall clock, max over ranks"},
+                        "call": "scftb_residual_batch (pinned host buffers), wall clock, max over ranks; bytes per rank"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "kernel": "march_ie_kernel<8,128,uniform>",
+                             "problems_per_launch": Pmax,
                              "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": march_ms_avg,
                              "peak_source": peak_src,
                              "bytes_per_dof_step": BYTES_PER_DOF_STEP}}
+        if weak:
+            line["weak"] = weak
+        assert max_rel_all < 1e-10, f"GPU results differ from the oracle: {max_rel_all:.3e}"
         if not args.no_cpu_baseline and world == 1:
             cores = host_cores()
-            cnt = max(cores, 8) * 256   # ~10-20 s of CPU work (16 threads: 4096 problems in ~11 s)
-            v, dt = oracle_throughput(cnt, cores)
+            v, dt = fair_cpu_throughput(0, total, cores)   # the WHOLE workload once: a few seconds on 16 threads
             line["cpu_baseline"] = {"value": v, "unit": "DOF-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"first {cnt} problems of the sweep, oracle/scft_oracle.c, {dt:.1f} s"}
-            probe = reference_code_probe()
-            if probe:
-                line["cpu_baseline"]["reference_code_probe"] = probe
+                                    "sample": f"all {total} problems of the sweep once, fair CPU port oracle/scft_fast.c "
+                                              f"(Thomas once per field, half history, SIMD over 8 problems), {dt:.1f} s"}
+            cnt = 4 * max(cores, 8)
+            cv, cdt = checker_throughput(cnt, cores)
+            line["cpu_baseline"]["checker_port"] = {"value": cv, "unit": "DOF-steps/s", "cores": cores,
+                                                    "sample": f"first {cnt} problems, oracle/scft_oracle.c (pivoting band LU, "
+                                                              f"full history; round 1's CPU arm), {cdt:.1f} s"}
+            rf = reference_faithful_leg()
+            if rf:
+                line["cpu_baseline"]["reference_faithful"] = rf
         _emit(line)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -56,7 +56,8 @@ typedef struct {
 int scftb_create(const scftb_config *cfg, scftb_engine **out);
 int scftb_destroy(scftb_engine *e);
 const char *scftb_last_error(void);
-/* number of kernels launched by the calling thread's engines since the last reset (bench evidence) */
+/* number of kernels this library launched in the PROCESS (all engines, all host threads) since the last reset
+ * (bench evidence) */
 long scftb_launch_count(int reset);
 
 /* Physical parameters of problem p (all problems when p < 0): surface-layer width tau, film
@@ -94,7 +95,10 @@ int scftb_free_energy(scftb_engine *e, int p, double f0bar, double *F);
  * scftb_callback_nr1 replaces SCFT_wrapper under #define BROYDN (drivescft.cc:218-243) and
  * simple_FEM_1D_transient as passed to broydn (1D_FEM.c:356): arrays in[1..n], out[1..n];
  * scftb_callback_c0 replaces SCFT_wrapper for adm_chen (0-based).  On a CUDA failure they set
- * scftb_funcerr (the analogue of broydn.c:25 funcerr) instead of aborting. */
+ * scftb_funcerr (the analogue of broydn.c:25 funcerr) instead of aborting.  The binding (and scftb_broydn's retained
+ * QR factors, the reference's caller-owned qt/r/d) is per HOST THREAD: each thread binds the engine it drives.
+ * March launches of one engine never overlap, whatever streams they are issued on: its history buffers belong to the
+ * resident CTA slots, so a launch on another stream is ordered after the previous one (cudaStreamWaitEvent). */
 int scftb_bind_global(scftb_engine *e);
 void scftb_callback_nr1(int n, double *in, double *out);
 void scftb_callback_c0(int n, double *in, double *out);
@@ -113,13 +117,15 @@ int scftb_adm_chen(scftb_func f, double *x_old, double tol, int maxIteration, in
 int scftb_adm(scftb_func f, double *x, int n, int *check, int maxits);
 /* broydn (broydn.c:44-292), x 0-based here; tolf in / achieved max|f| out via *err; jc as in
  * broydn.c:26-27.  When f == scftb_callback_c0 the finite-difference Jacobian (fdjac.c:18-34)
- * is evaluated as ONE batch of n residuals on the device. */
+ * is evaluated as ONE batch of n residuals on the device, all with the parameters of problem 0 of the bound engine
+ * (the problem the callback evaluates) — safe on a sweep engine whose slots hold different (tau, L). */
 int scftb_broydn(scftb_func f, double *x, int n, int *check, double *err, int *jc);
 
 /* broydn with EVERYTHING on the device: finite-difference Jacobian as one batched launch, Householder QR,
  * Q^T, Givens rank-one updates, triangular solves and line-search vectors stay in HBM; the host steers with a
- * few scalars per step.  Solves problem 0 of the engine, whose first N-2 problems must share its (tau, L, mesh)
- * (scftb_set_problem(e, -1, ...)); x[N-2] host in/out; check / err / jc as scftb_broydn. */
+ * few scalars per step.  Solves problem 0 of the engine; the Jacobian columns are evaluated with problem 0's
+ * (tau, L, mesh) in batches of max_batch fields, whatever parameters the other slots of the engine hold (their phi, Q,
+ * eta_full are not touched).  x[N-2] host in/out; check / err / jc as scftb_broydn. */
 int scftb_broydn_device(scftb_engine *e, double *x, int *check, double *err, int *jc);
 /* Same with options.  SCFTB_BROYDN_KEEP_TRIAL: when the line search stops on its step-size test
  * (lnsrch.c: alam < alamin) the reference resets x to the previous iterate but reports the residual norm of
@@ -169,6 +175,8 @@ int scftb_mixer_iterate_device(scftb_mixer *m, void *stream);
 /* done[p]: 0 running, 1 converged, 2 NaN; iters[p]: iteration index at which it stopped; err[p]: last max|F| */
 int scftb_mixer_status(scftb_mixer *m, void *stream, int *done, int *iters, double *err);
 int scftb_mixer_get_x(scftb_mixer *m, void *stream, double *x /* host [nprob][N-2] */);
+/* residuals Y_k = F(X_k) of iteration k (ADM_chen_C.c:50,57), still in the ring while k > iterations issued - nn - 2 */
+int scftb_mixer_get_y(scftb_mixer *m, void *stream, int k, double *y /* host [nprob][N-2] */);
 
 /* ---- around the hot path: spline, refinement, result files ------------------- */
 /* spline_chen (spline_chen.c:12-106): mode 0 natural (m = 0), 1 not-a-knot (m == NULL), 2 y'' = bc at both
@@ -232,6 +240,8 @@ int scftb2d_export_csr(scftb2d_engine *e, int *rowptr, int *colind, double *valT
  * scftb_get_march_ms returns the summed device time and the number of launches since the last call. */
 int scftb_set_timing(scftb_engine *e, int on);
 int scftb_get_march_ms(scftb_engine *e, double *total_ms, int *count);
+/* resident CTA slots of the march kernel on this device (= problems per wave; lean history is kept per slot) */
+int scftb_get_slots(scftb_engine *e, int *slots);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,9 @@ def lib():
                                    _dp, C.POINTER(C.c_int)]
         L.orc_adm.restype = C.c_int
         L.orc_adm.argtypes = [FUNC, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int)]
+        L.orc_fast_sweep.restype = C.c_int
+        L.orc_fast_sweep.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp,
+                                     C.c_int]
         _lib = L
     return _lib
 
@@ -139,6 +142,23 @@ def residual(eta_full_, f0, scheme=IE_CONSISTENT, nsteps=2048, L=L_REF, x=None, 
     if want_hist:
         r["hist"] = hist
     return r
+
+
+def fast_sweep(taus, Ls, eta_mid, N, scheme=IE_ROWSCALE, nsteps=2048, quadrature=QUAD_ROMBERG, sign=1.0, threads=1,
+               want_phi=True):
+    """The "fair CPU" baseline (oracle/scft_fast.c): Thomas once per field, half history, 8 problems interleaved for
+    SIMD, `threads` POSIX threads.  eta_mid [nprob, N-2] -> dict(out [nprob, N-2], phi [nprob, N], Q [nprob])."""
+    taus, Ls, eta_mid = _arr(taus), _arr(Ls), _arr(eta_mid)
+    nprob = len(taus)
+    assert eta_mid.shape == (nprob, N - 2)
+    out = np.zeros((nprob, N - 2))
+    phi = np.zeros((nprob, N)) if want_phi else None
+    Q = np.zeros(nprob)
+    rc = lib().orc_fast_sweep(nprob, N, nsteps, scheme, quadrature, sign, _p(taus), _p(Ls), _p(eta_mid), _p(out),
+                              _p(phi) if want_phi else None, _p(Q), int(threads))
+    if rc:
+        raise ValueError("orc_fast_sweep: IE schemes on uniform meshes only (Romberg needs nsteps = 2^k >= 16)")
+    return dict(out=out, phi=phi, Q=Q)
 
 
 def residual_ab(etaA_full, etaB_full, jf, chiN, f0, scheme=IE_ROWSCALE, nsteps=2048, L=L_REF, x=None,
@@ -216,6 +236,8 @@ def ref():
         R.ref_adm_chen.argtypes = [FUNC, _dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
         R.ref_broydn.restype = C.c_int
         R.ref_broydn.argtypes = [FUNC, _dp, C.c_int, C.c_double, _dp, C.POINTER(C.c_int)]
+        R.ref_broydn_raw.restype = C.c_int
+        R.ref_broydn_raw.argtypes = [C.c_void_p, _dp, C.c_int, C.c_double, _dp, C.POINTER(C.c_int)]
         _ref = R
     return _ref
 
@@ -261,6 +283,24 @@ def ref_broydn(pyfunc, x0, tolf, jc=0):
     jcv = C.c_int(jc)
     check = ref().ref_broydn(_wrap(pyfunc, len(x)), _p(x), len(x), tolf, C.byref(err), C.byref(jcv))
     return check, x, err.value, jcv.value
+
+
+def ref_broydn_raw(fn_addr, x0, tolf, jc=0):
+    """the reference's broydn.c driving a RAW C callback (address of a void f(int, double[1..n], double[1..n]),
+    e.g. scftb_callback_nr1) — no Python or C adapter between the reference and the callback"""
+    x = _arr(x0).copy()
+    err = C.c_double(0)
+    jcv = C.c_int(jc)
+    check = ref().ref_broydn_raw(C.c_void_p(fn_addr), _p(x), len(x), tolf, C.byref(err), C.byref(jcv))
+    return check, x, err.value, jcv.value
+
+
+def ref_adm_chen_raw(fn_addr, x0, tol, max_iteration, lmd, nn, final=False):
+    """the reference's adm_chen (ADM_chen_C.c:18) driving a RAW 0-based C callback (e.g. scftb_callback_c0)"""
+    x = _arr(x0).copy()
+    f = C.cast(C.c_void_p(fn_addr), FUNC)   # a function-pointer VALUE: ctypes passes the address itself
+    rc = ref().ref_adm_chen(f, _p(x), tol, max_iteration, len(x), lmd, nn, int(final))
+    return rc, x
 
 
 def ref_adm(pyfunc, x0):

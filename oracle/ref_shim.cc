@@ -76,4 +76,25 @@ int ref_broydn(void (*f)(int, double*, double*), double* x, int n, double tolf, 
   free_dvector(d, 1, n);
   return check;
 }
+
+// The reference's broydn handed a RAW residual callback of the reference's own shape
+// void f(int n, double in[1..n], double out[1..n]) (broydn.c:44-46, fdjac.c:10-11) — e.g. the address of
+// scftb_callback_nr1 — with no adapter in between: this is the call drivescft.cc:301 / 1D_FEM.c:356 makes.
+// x is 0-based here and shifted the way NR callers do (x-1).
+int ref_broydn_raw(void (*vecfunc)(int, double[], double[]), double* x, int n, double tolf, double* err_out, int* jc_io) {
+  qt = dmatrix(1, n, 1, n);
+  r = dmatrix(1, n, 1, n);
+  d = dvector(1, n);
+  jc = jc_io ? *jc_io : 0;
+  err = tolf;
+  funcerr = 0;
+  int check = 1;
+  broydn(x - 1, n, &check, vecfunc);
+  if (err_out) *err_out = err;
+  if (jc_io) *jc_io = jc;
+  free_dmatrix(qt, 1, n, 1, n);
+  free_dmatrix(r, 1, n, 1, n);
+  free_dvector(d, 1, n);
+  return check;
+}
 }

@@ -95,6 +95,11 @@ int orc_adm_chen(orc_func f, double *x, double tol, int maxIteration, int n, dou
 /* Anderson mixing for x=f(x) (adm.c:24-313), 0-based, err=1e-10, NRMAX=10. */
 int orc_adm(orc_func f, double *x, int n, int maxits, double *trace, int *iters);
 
+/* scft_fast.c — the "fair CPU" baseline: Thomas factorisation once per field, half history, VL problems interleaved
+ * for SIMD, POSIX threads over groups of problems.  IE schemes, uniform meshes.  Checked against orc_residual in tests/. */
+int orc_fast_sweep(int nprob, int N, int nsteps, int scheme, int quadrature, double sign, const double *tau,
+                   const double *L, const double *eta_mid, double *out, double *phi_out, double *Q_out, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

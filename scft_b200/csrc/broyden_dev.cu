@@ -395,9 +395,9 @@ extern "C" int scftb_broydn_device_ex(scftb_engine *e, double *x_host, int *chec
       const int B = e->cfg.max_batch;
       for (int j0 = 0; j0 < n; j0 += B) {
         const int nb = std::min(B, n - j0);
-        if ((rc = launch_march(e, nb, g_bd.xb + (size_t)j0 * n, n, g_bd.fb + (size_t)j0 * n, n, nullptr, st))) return rc;
+        // pshare: all columns with problem 0's (tau, L, mesh); the other slots' parameters and outputs are not involved
+        if ((rc = launch_march(e, nb, g_bd.xb + (size_t)j0 * n, n, g_bd.fb + (size_t)j0 * n, n, nullptr, st, 0, true))) return rc;
       }
-      // the batch overwrote the engine's per-problem outputs of problem 0 (phi, Q); fvec itself is separate
       jac_form_kernel<<<GNN, 256, 0, st>>>(n, g_bd.fb, fvec, hs, r);
       {
         int nn_ = n;

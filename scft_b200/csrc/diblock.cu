@@ -126,7 +126,7 @@ int ensure_kernel(scftb_engine *e, DiblockState *s) {
   return SCFTB_OK;
 }
 
-int launch_ab(scftb_engine *e, DiblockState *s, int nprob, const double *d_w, double *d_out, cudaStream_t st) {
+int launch_ab(scftb_engine *e, DiblockState *s, int nprob, const double *d_w, double *d_out, cudaStream_t st, bool pshare = false) {
   int rc = ensure_kernel(e, s);
   if (rc) return rc;
   if (s->chi_dirty) {
@@ -136,7 +136,7 @@ int launch_ab(scftb_engine *e, DiblockState *s, int nprob, const double *d_w, do
   MarchParams P{};
   P.N = e->cfg.N; P.ni = e->ni; P.nsteps = e->cfg.nsteps;
   P.scheme = e->cfg.scheme; P.nprob = nprob; P.store_full = 0;
-  P.uniform = e->uniform ? 1 : 0; P.sign = e->cfg.sign;
+  P.uniform = e->uniform ? 1 : 0; P.sign = e->cfg.sign; P.pshare = pshare ? 1 : 0;
   P.eta_mid = d_w; P.eta_stride = 2 * (long long)e->ni; P.out_stride = 2 * (long long)e->ni; P.skip = nullptr;
   P.f0 = e->d_f0; P.L = e->d_L; P.x = e->d_x; P.eta_bnd = e->d_eta_bnd; P.w = e->d_w;
   P.hist = s->d_hist; P.hist_stride = (long long)(e->cfg.nsteps + 1) * (long long)s->SL;
@@ -148,10 +148,11 @@ int launch_ab(scftb_engine *e, DiblockState *s, int nprob, const double *d_w, do
       CK(cudaMalloc(&s->d_scratch, sizeof(double) * 2 * e->ni * e->cfg.max_batch));
       P.eta_bndB = s->d_eta_bndB;
     }
-    spline_bnd_launch(nprob, P.N, e->d_x, d_w, P.eta_stride, e->d_scratch, e->d_eta_bnd, st);
-    spline_bnd_launch(nprob, P.N, e->d_x, d_w + e->ni, P.eta_stride, s->d_scratch, s->d_eta_bndB, st);
+    spline_bnd_launch(nprob, P.N, e->d_x, d_w, P.eta_stride, e->d_scratch, e->d_eta_bnd, st, P.pshare);
+    spline_bnd_launch(nprob, P.N, e->d_x, d_w + e->ni, P.eta_stride, s->d_scratch, s->d_eta_bndB, st, P.pshare);
   }
   const int grid = std::min(nprob, s->slots);
+  if ((rc = order_before_launch(e, st))) return rc;
   std::pair<cudaEvent_t, cudaEvent_t> ev;
   if (e->timing) {   // same per-launch CUDA-event timing as the one-sweep march (scftb_set_timing / scftb_get_march_ms)
     if (!e->ev_free.empty()) { ev = e->ev_free.back(); e->ev_free.pop_back(); }
@@ -162,7 +163,7 @@ int launch_ab(scftb_engine *e, DiblockState *s, int nprob, const double *d_w, do
   if (e->timing) { CK(cudaEventRecord(ev.second, st)); e->ev_pending.push_back(ev); }
   g_launches++;
   CK(cudaGetLastError());
-  return SCFTB_OK;
+  return note_launch(e, st);
 }
 
 }  // namespace
@@ -179,7 +180,7 @@ int scftb_set_diblock(scftb_engine *e, int p, double fA, double chiN) {
   return SCFTB_OK;
 }
 
-int scftb_residual_ab_batch(scftb_engine *e, int nprob, const double *w, double *out) {
+static int residual_ab_impl(scftb_engine *e, int nprob, const double *w, double *out, bool pshare) {
   if (!e || !w || !out || nprob < 1 || nprob > e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "nprob out of range");
   DiblockState *s = (DiblockState *)e->diblock_state;
   if (!s) return fail(SCFTB_ERR_STATE, "scftb_set_diblock has not been called on this engine");
@@ -188,12 +189,23 @@ int scftb_residual_ab_batch(scftb_engine *e, int nprob, const double *w, double 
   if (rc) return rc;
   const size_t bytes = sizeof(double) * 2 * (size_t)e->ni * nprob;
   CK(cudaMemcpyAsync(s->d_w, w, bytes, cudaMemcpyHostToDevice, e->stream));
-  rc = launch_ab(e, s, nprob, s->d_w, s->d_out, e->stream);
+  rc = launch_ab(e, s, nprob, s->d_w, s->d_out, e->stream, pshare);
   if (rc) return rc;
   CK(cudaMemcpyAsync(out, s->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return SCFTB_OK;
 }
+
+int scftb_residual_ab_batch(scftb_engine *e, int nprob, const double *w, double *out) {
+  return residual_ab_impl(e, nprob, w, out, false);
+}
+}  // extern "C"
+namespace scftb {
+int residual_ab_batch_shared(scftb_engine *e, int nprob, const double *w, double *out) {
+  return residual_ab_impl(e, nprob, w, out, true);
+}
+}  // namespace scftb
+extern "C" {
 
 int scftb_residual_ab(scftb_engine *e, const double *w, double *out) { return scftb_residual_ab_batch(e, 1, w, out); }
 

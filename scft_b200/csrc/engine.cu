@@ -83,11 +83,12 @@ void f0_given(int N, const double *x, double tau, double *f0) {
 // problem runs Thomas over the N-2 knots.  Uniform meshes never need this (see eta_node()).
 // ---------------------------------------------------------------------------------------------
 __global__ void spline_bnd_kernel(int nprob, int N, const double *x, const double *eta_mid, long long eta_stride,
-                                  double *scratch, double *eta_bnd) {
+                                  double *scratch, double *eta_bnd, int pshare) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nprob) return;
   const int Nx = N - 2;
-  const double *xk = x + (size_t)p * N + 1;  // knots = interior nodes
+  x += (size_t)(pshare ? 0 : p) * N;         // mesh of this problem (pshare: every problem on the mesh of slot 0)
+  const double *xk = x + 1;                  // knots = interior nodes
   const double *y = eta_mid + (size_t)p * eta_stride;
   double *cp = scratch + (size_t)p * 2 * Nx, *dp = cp + Nx;
   // rows i=1..Nx-2: (x_i-x_{i-1})/6, (x_{i+1}-x_{i-1})/3, (x_{i+1}-x_i)/6 ; rows 0, Nx-1: M = 0
@@ -105,7 +106,7 @@ __global__ void spline_bnd_kernel(int nprob, int N, const double *x, const doubl
     if (i == Nx - 2) Mlast1 = Mn;
     if (i == 1) M1 = Mn;
   }
-  const double *xf = x + (size_t)p * N;
+  const double *xf = x;
   {  // left wall: klo=0, khi=1
     double h = xk[1] - xk[0], a = (xk[1] - xf[0]) / h, b = (xf[0] - xk[0]) / h;
     eta_bnd[2 * p] = a * y[0] + b * y[1] + ((a * a * a - a) * 0.0 + (b * b * b - b) * M1) * (h * h) / 6.0;
@@ -118,8 +119,8 @@ __global__ void spline_bnd_kernel(int nprob, int N, const double *x, const doubl
 }
 
 void spline_bnd_launch(int nprob, int N, const double *x, const double *eta_mid, long long eta_stride, double *scratch,
-                       double *eta_bnd, cudaStream_t st) {
-  spline_bnd_kernel<<<(nprob + 63) / 64, 64, 0, st>>>(nprob, N, x, eta_mid, eta_stride, scratch, eta_bnd);
+                       double *eta_bnd, cudaStream_t st, int pshare) {
+  spline_bnd_kernel<<<(nprob + 63) / 64, 64, 0, st>>>(nprob, N, x, eta_mid, eta_stride, scratch, eta_bnd, pshare);
   g_launches++;
 }
 
@@ -230,6 +231,8 @@ int scftb_create(const scftb_config *cfg, scftb_engine **out) {
   e->last_nprob = 0;
   e->timing = false;
   e->d_x = e->d_eta_bnd = e->d_scratch = nullptr;
+  e->d_eta = e->d_out = e->d_phi = e->d_Q = e->d_f0 = e->d_L = e->d_w = e->d_hist = e->d_eta_full = nullptr;
+  e->stream = nullptr;
   const int N = cfg->N, B = cfg->max_batch, n = cfg->nsteps;
   if (cfg->quadrature == SCFTB_QUAD_ROMBERG) {
     if (romberg_weights(n, 1.0 / n, e->h_w)) {
@@ -244,14 +247,16 @@ int scftb_create(const scftb_config *cfg, scftb_engine **out) {
   for (int j = 0; j <= n; j++) wq[j] = (2 * j > n) ? 2.0 * e->h_w[j] : ((2 * j == n) ? e->h_w[j] : 0.0);
   if (choose_any(cfg->scheme, e->ni, true, e->kc, cfg->nsteps)) {
     delete e;
-    return fail(SCFTB_ERR_ARG, "N too large for the register-resident march (N <= 4098 in this build)");
+    return fail(SCFTB_ERR_ARG, cfg->scheme == SCFTB_IRK4_CONSISTENT
+                                   ? "N too large for the register-resident IRK4 march (N <= 2050 in this build)"
+                                   : "N too large for the register-resident march (N <= 4098 in this build)");
   }
 #define CKD(call)                                                                                  \
   do {                                                                                             \
     cudaError_t _e = (call);                                                                       \
     if (_e != cudaSuccess) {                                                                       \
       int rc = fail(SCFTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));           \
-      delete e;                                                                                    \
+      scftb_destroy(e); /* frees whatever was allocated so far (members start out null) */         \
       return rc;                                                                                   \
     }                                                                                              \
   } while (0)
@@ -306,22 +311,29 @@ int scftb_get_march_ms(scftb_engine *e, double *total_ms, int *count) {
 
 int scftb_engine_max_batch(scftb_engine *e) { return e ? e->cfg.max_batch : 0; }
 
+int scftb_get_slots(scftb_engine *e, int *slots) {
+  if (!e || !slots) return fail(SCFTB_ERR_ARG, "null argument");
+  *slots = e->slots;
+  return SCFTB_OK;
+}
+
 int scftb_destroy(scftb_engine *e) {
   if (!e) return SCFTB_OK;
   scftb_unbind_engine(e);
   cudaSetDevice(e->cfg.device);
-  cudaStreamSynchronize(e->stream);
+  if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->solver_state && e->solver_state_free) e->solver_state_free(e->solver_state);
   if (e->diblock_state && e->diblock_state_free) e->diblock_state_free(e->diblock_state);
   for (double *p : {e->d_eta, e->d_out, e->d_phi, e->d_Q, e->d_f0, e->d_L, e->d_x, e->d_eta_bnd, e->d_w, e->d_hist,
                     e->d_eta_full, e->d_scratch})
     if (p) cudaFree(p);
   for (cudaEvent_t ev : e->ev_pipe) cudaEventDestroy(ev);
+  if (e->ev_last) cudaEventDestroy(e->ev_last);
   for (auto &ev : e->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   for (auto &ev : e->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (e->s_in) cudaStreamDestroy(e->s_in);
   if (e->s_out) cudaStreamDestroy(e->s_out);
-  cudaStreamDestroy(e->stream);
+  if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return SCFTB_OK;
 }
@@ -351,13 +363,24 @@ int scftb_set_problem(scftb_engine *e, int p, double tau, double L, const double
 }  // extern "C"
 
 namespace scftb {
+int order_before_launch(scftb_engine *e, cudaStream_t st) {
+  if (e->have_last && e->st_last != st) CK(cudaStreamWaitEvent(st, e->ev_last, 0));
+  return SCFTB_OK;
+}
+int note_launch(scftb_engine *e, cudaStream_t st) {
+  if (!e->ev_last) CK(cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming));
+  CK(cudaEventRecord(e->ev_last, st));
+  e->st_last = st; e->have_last = true;
+  return SCFTB_OK;
+}
+
 int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_stride, double *d_out,
-                 long long out_stride, const int *d_skip, cudaStream_t st, int p0) {
+                 long long out_stride, const int *d_skip, cudaStream_t st, int p0, bool pshare) {
   MarchParams P{};
   const size_t N = e->cfg.N, o = (size_t)p0;
   P.N = e->cfg.N; P.ni = e->ni; P.nsteps = e->cfg.nsteps;
   P.scheme = e->cfg.scheme; P.nprob = nprob; P.store_full = e->cfg.store_history;
-  P.uniform = e->uniform ? 1 : 0; P.sign = e->cfg.sign;
+  P.uniform = e->uniform ? 1 : 0; P.sign = e->cfg.sign; P.pshare = pshare ? 1 : 0;
   P.eta_mid = d_eta; P.eta_stride = eta_stride; P.out_stride = out_stride; P.skip = d_skip;
   P.f0 = e->d_f0 + o * N; P.L = e->d_L + o; P.w = e->d_w;
   P.x = e->d_x ? e->d_x + o * N : nullptr; P.eta_bnd = e->d_eta_bnd ? e->d_eta_bnd + 2 * o : nullptr;
@@ -366,10 +389,14 @@ int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_
   P.out = d_out; P.phi = e->d_phi + o * N; P.Q = e->d_Q + o; P.eta_full = e->d_eta_full + o * N;
   if (!e->uniform) {
     spline_bnd_kernel<<<(nprob + 63) / 64, 64, 0, st>>>(nprob, P.N, P.x, d_eta, eta_stride, e->d_scratch + o * 2 * e->ni,
-                                                          e->d_eta_bnd + 2 * o);
+                                                          e->d_eta_bnd + 2 * o, P.pshare);
     g_launches++;
   }
   int grid = std::min(nprob, e->slots);
+  {
+    int rc = order_before_launch(e, st);
+    if (rc) return rc;
+  }
   std::pair<cudaEvent_t, cudaEvent_t> ev;
   if (e->timing) {
     if (!e->ev_free.empty()) { ev = e->ev_free.back(); e->ev_free.pop_back(); }
@@ -381,7 +408,7 @@ int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_
   g_launches++;
   CK(cudaGetLastError());
   e->last_nprob = nprob;
-  return SCFTB_OK;
+  return note_launch(e, st);
 }
 }  // namespace scftb
 
@@ -448,6 +475,26 @@ int scftb_residual_batch(scftb_engine *e, int nprob, const double *eta_mid, doub
 }
 
 int scftb_residual(scftb_engine *e, const double *eta_mid, double *out) { return scftb_residual_batch(e, 1, eta_mid, out); }
+
+}  // extern "C"
+
+namespace scftb {
+int residual_batch_shared(scftb_engine *e, int nprob, const double *eta_mid, double *out) {
+  if (!e || nprob < 1 || nprob > e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "nprob out of range");
+  CK(cudaSetDevice(e->cfg.device));
+  int rc = upload_params(e);
+  if (rc) return rc;
+  const size_t bytes = sizeof(double) * (size_t)e->ni * nprob;
+  CK(cudaMemcpyAsync(e->d_eta, eta_mid, bytes, cudaMemcpyHostToDevice, e->stream));
+  rc = launch_march(e, nprob, e->d_eta, e->ni, e->d_out, e->ni, nullptr, e->stream, 0, true);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return SCFTB_OK;
+}
+}  // namespace scftb
+
+extern "C" {
 
 static int fetch(scftb_engine *e, const double *d, size_t off, size_t cnt, double *h) {
   CK(cudaSetDevice(e->cfg.device));

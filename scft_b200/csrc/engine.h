@@ -27,7 +27,7 @@ struct KernelChoice {
 extern std::atomic<long> g_launches;
 int choose_kernel(int ni, bool uni, KernelChoice &kc, bool odd);
 void spline_bnd_launch(int nprob, int N, const double *x, const double *eta_mid, long long eta_stride, double *scratch,
-                       double *eta_bnd, cudaStream_t st);
+                       double *eta_bnd, cudaStream_t st, int pshare = 0);
 }  // namespace scftb
 
 #define CK(call)                                                                                   \
@@ -53,6 +53,11 @@ struct scftb_engine {
   int last_nprob;
   // device buffers
   double *d_eta, *d_out, *d_phi, *d_Q, *d_f0, *d_L, *d_x, *d_eta_bnd, *d_w, *d_hist, *d_eta_full, *d_scratch;
+  // lean history lives per resident CTA slot of THIS engine, so two march launches of one engine must never overlap:
+  // every launch records ev_last on its stream and a launch on a different stream first waits on it
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t st_last = nullptr;
+  bool have_last = false;
   // optional per-launch timing of the march kernel (CUDA events on the launching stream)
   bool timing;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
@@ -70,9 +75,18 @@ struct scftb_engine {
 namespace scftb {
 // launch one batch of residual evaluations; eta/out are device pointers with the given problem strides
 // p0: index of the first problem of this launch in the engine's per-problem arrays (d_eta / d_out already point at it)
+// pshare: every problem of the launch is evaluated with the parameters (tau, L, mesh, phi_0) of slot p0 and only `out` is
+// written — the n perturbed fields of a finite-difference Jacobian (fdjac.c:18-34) of ONE problem, whatever the other
+// slots of the engine hold
 int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_stride, double *d_out,
-                 long long out_stride, const int *d_skip, cudaStream_t st, int p0 = 0);
+                 long long out_stride, const int *d_skip, cudaStream_t st, int p0 = 0, bool pshare = false);
+// host-buffer batch of nprob fields of problem 0 (pshare launch), for the host-flow solvers
+int residual_batch_shared(scftb_engine *e, int nprob, const double *eta_mid, double *out);
+int residual_ab_batch_shared(scftb_engine *e, int nprob, const double *w, double *out);
 int upload_params(scftb_engine *e);
+// order a march launch on `st` after the engine's previous march launch (no-op on the same stream) / note it
+int order_before_launch(scftb_engine *e, cudaStream_t st);
+int note_launch(scftb_engine *e, cudaStream_t st);
 }  // namespace scftb
 
 // internal accessor (not part of the public ABI)

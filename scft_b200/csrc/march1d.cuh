@@ -36,6 +36,8 @@ struct MarchParams {
   int nprob;              // problems in this launch
   int store_full;         // 1: store every slice, per problem; 0: half history, per CTA slot
   int uniform;            // 1: uniform mesh (x == nullptr)
+  int pshare;             // 1: every problem of the launch uses parameter slot 0 (f0, L, x, chi) and writes only `out`
+                          //    (the columns of a finite-difference Jacobian, fdjac.c:18-34); 0: problem p uses slot p
   double sign;
   const double *eta_mid;  // [nprob][ni], problem stride eta_stride
   long long eta_stride;   // doubles between consecutive problems in eta_mid
@@ -120,7 +122,7 @@ __device__ __forceinline__ Row assemble_row(const MarchParams &P, int p, int g, 
     r.Al = h / 6; r.Ad = 2. / 3 * h; r.Au = h / 6;
     bl = -1 / h; bd = 2. / h; bu = -1 / h;
   } else {          // simple_FEM_1D_transient.m:35-57
-    const double *x = P.x + (size_t)p * P.N;
+    const double *x = P.x + (size_t)(P.pshare ? 0 : p) * P.N;
     a1 = x[i] - x[i - 1]; a2 = x[i + 1] - x[i];
     r.Al = a1 / 6; r.Ad = a1 / 3 + a2 / 3; r.Au = a2 / 6;
     bl = -1 / a1; bd = 1 / a1 + 1 / a2; bu = -1 / a2;
@@ -182,7 +184,8 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
 
   for (int p = blockIdx.x; p < P.nprob; p += gridDim.x) {
     if (P.skip && P.skip[p]) continue;
-    const double L = P.L[p];
+    const int pp = P.pshare ? 0 : p;      // parameter slot
+    const double L = P.L[pp];
     // state that lives across the segments of a two-species march (one segment otherwise)
     double q[C], phi[C], phiB[TWO ? C : 1];
     double XL, qn, qsumF = 0.0;
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
           const int i = g + 1;
           double hw2;
           if (P.uniform) { double h = L / (P.N - 1); hw2 = 0.5 * (h + h); }
-          else { const double *x = P.x + (size_t)p * P.N; hw2 = 0.5 * ((x[i] - x[i - 1]) + (x[i + 1] - x[i])); }
+          else { const double *x = P.x + (size_t)pp * P.N; hw2 = 0.5 * ((x[i] - x[i - 1]) + (x[i + 1] - x[i])); }
           qsumF += hw2 * q[k];
         }
       }
@@ -574,21 +577,23 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     // ------------------------------------------------------------------ residual, phi, Q
     double qsum = 0.0;
     if constexpr (TWO) {
-      const double chi = P.chi[p];
+      const double chi = P.chi[pp];
       const double *em = P.eta_mid + (size_t)p * P.eta_stride;
 #pragma unroll
       for (int k = 0; k < C; k++) {
         const int g = t * C + k;
         if (g < P.ni) {
           const int i = g + 1;
-          const double f0 = P.f0[(size_t)p * P.N + i], pa = phi[k], pb = phiB[TWO ? k : 0];
+          const double f0 = P.f0[(size_t)pp * P.N + i], pa = phi[k], pb = phiB[TWO ? k : 0];
           P.out[(size_t)p * P.out_stride + g] = P.sign * (f0 - pa - pb);
           P.out[(size_t)p * P.out_stride + P.ni + g] = em[g] - em[P.ni + g] - chi * (pb - pa);
-          P.phi[(size_t)p * P.N + i] = pa;
-          P.phiB[(size_t)p * P.N + i] = pb;
+          if (!P.pshare) {
+            P.phi[(size_t)p * P.N + i] = pa;
+            P.phiB[(size_t)p * P.N + i] = pb;
+          }
         }
       }
-      if (t == 0) {
+      if (t == 0 && !P.pshare) {
         P.phi[(size_t)p * P.N] = 0.0; P.phi[(size_t)p * P.N + P.N - 1] = 0.0;
         P.phiB[(size_t)p * P.N] = 0.0; P.phiB[(size_t)p * P.N + P.N - 1] = 0.0;
       }
@@ -599,17 +604,17 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
       const int g = t * C + k;
       if (g < P.ni) {
         const int i = g + 1;
-        const double f0 = P.f0[(size_t)p * P.N + i];
+        const double f0 = P.f0[(size_t)pp * P.N + i];
         P.out[(size_t)p * P.out_stride + g] = P.sign * (f0 - phi[k]);
-        P.phi[(size_t)p * P.N + i] = phi[k];
+        if (!P.pshare) P.phi[(size_t)p * P.N + i] = phi[k];
         double hw2;
         if (P.uniform) { double h = L / (P.N - 1); hw2 = 0.5 * (h + h); }
-        else { const double *x = P.x + (size_t)p * P.N; hw2 = 0.5 * ((x[i] - x[i - 1]) + (x[i + 1] - x[i])); }
+        else { const double *x = P.x + (size_t)pp * P.N; hw2 = 0.5 * ((x[i] - x[i - 1]) + (x[i + 1] - x[i])); }
         qsum += hw2 * q[k];
-        if (P.eta_full) P.eta_full[(size_t)p * P.N + i] = P.eta_mid[(size_t)p * P.eta_stride + g];
+        if (P.eta_full && !P.pshare) P.eta_full[(size_t)p * P.N + i] = P.eta_mid[(size_t)p * P.eta_stride + g];
       }
     }
-    if (t == 0) {
+    if (t == 0 && !P.pshare) {
       P.phi[(size_t)p * P.N] = 0.0; P.phi[(size_t)p * P.N + P.N - 1] = 0.0;
       if (P.eta_full) {
         P.eta_full[(size_t)p * P.N] = eta_node(P, p, 0, L);
@@ -621,10 +626,10 @@ __global__ void __launch_bounds__(T, MINB) march_ie_kernel(MarchParams P) {
     for (int d = 16; d > 0; d >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, d);
     if (lane == 0) s_red[wid] = qsum;
     __syncthreads();
-    if (t == 0) {
+    if (t == 0 && !P.pshare) {
       double s = 0.0;
       for (int w = 0; w < NW; w++) s += s_red[w];
-      double len = P.uniform ? L : (P.x[(size_t)p * P.N + P.N - 1] - P.x[(size_t)p * P.N]);
+      double len = P.uniform ? L : (P.x[(size_t)pp * P.N + P.N - 1] - P.x[(size_t)pp * P.N]);
       P.Q[p] = s / len;
     }
   }

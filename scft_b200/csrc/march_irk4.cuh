@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
 
   for (int p = blockIdx.x; p < P.nprob; p += gridDim.x) {
     if (P.skip && P.skip[p]) continue;
-    const double L = P.L[p];
+    const int pp = P.pshare ? 0 : p;      // parameter slot (MarchParams::pshare)
+    const double L = P.L[pp];
     auto wrow = [&](const Row &r, cx &wl, cx &wd, cx &wu) {   // W = z1 A + dt D
       wl = mk(fma(dt, r.Dl, z1.re * r.Al), z1.im * r.Al);
       wd = mk(fma(dt, r.Dd, z1.re * r.Ad), z1.im * r.Ad);
@@ -296,17 +297,17 @@ __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
       const int g = t * C + k;
       if (g < P.ni) {
         const int i = g + 1;
-        const double f0 = P.f0[(size_t)p * P.N + i];
+        const double f0 = P.f0[(size_t)pp * P.N + i];
         P.out[(size_t)p * P.out_stride + g] = P.sign * (f0 - phi[k]);
-        P.phi[(size_t)p * P.N + i] = phi[k];
+        if (!P.pshare) P.phi[(size_t)p * P.N + i] = phi[k];
         double hw2;
         if (P.uniform) { double h = L / (P.N - 1); hw2 = 0.5 * (h + h); }
-        else { const double *x = P.x + (size_t)p * P.N; hw2 = 0.5 * ((x[i] - x[i - 1]) + (x[i + 1] - x[i])); }
+        else { const double *x = P.x + (size_t)pp * P.N; hw2 = 0.5 * ((x[i] - x[i - 1]) + (x[i + 1] - x[i])); }
         qsum += hw2 * q[k];
-        if (P.eta_full) P.eta_full[(size_t)p * P.N + i] = P.eta_mid[(size_t)p * P.eta_stride + g];
+        if (P.eta_full && !P.pshare) P.eta_full[(size_t)p * P.N + i] = P.eta_mid[(size_t)p * P.eta_stride + g];
       }
     }
-    if (t == 0) {
+    if (t == 0 && !P.pshare) {
       P.phi[(size_t)p * P.N] = 0.0; P.phi[(size_t)p * P.N + P.N - 1] = 0.0;
       if (P.eta_full) {
         P.eta_full[(size_t)p * P.N] = eta_node(P, p, 0, L);
@@ -317,10 +318,10 @@ __global__ void __launch_bounds__(T) march_irk4_kernel(MarchParams P) {
     for (int d = 16; d > 0; d >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, d);
     if (lane == 0) s_red[wid] = qsum;
     __syncthreads();
-    if (t == 0) {
+    if (t == 0 && !P.pshare) {
       double s = 0.0;
       for (int w = 0; w < NW; w++) s += s_red[w];
-      double len = P.uniform ? L : (P.x[(size_t)p * P.N + P.N - 1] - P.x[(size_t)p * P.N]);
+      double len = P.uniform ? L : (P.x[(size_t)pp * P.N + P.N - 1] - P.x[(size_t)pp * P.N]);
       P.Q[p] = s / len;
     }
   }

@@ -73,7 +73,11 @@ __global__ void __launch_bounds__(AND_THREADS) anderson_kernel(AndersonParams A)
   __syncthreads();
   if (tid == 0) A.err[p] = bad ? nan("") : err;
   if (bad) {   // the reference exit(1)s here; frozen unless the caller asked to keep evaluating (benchmarks)
-    if (tid == 0 && A.done[p] == 0) { A.done[p] = 2; A.iters[p] = k; }
+    if (A.done[p] == 0) {   // keep the field whose residual first went NaN: scftb_mixer_get_x returns it
+      for (int i = tid; i < n; i += AND_THREADS) A.xfinal[(size_t)p * n + i] = Xk[i];
+      __syncthreads();
+      if (tid == 0) { A.done[p] = 2; A.iters[p] = k; }
+    }
     if (A.freeze) return;
   }
   if (err < A.tol) {                       // converged: x_old = X[k] (ADM_chen_C.c:71-84)
@@ -257,9 +261,14 @@ int scftb_mixer_create(scftb_engine *e, int nprob, double tol, double lmd, int n
   CKM(cudaMalloc(&m->k_restart, sizeof(int) * nprob));
   CKM(cudaMalloc(&m->done, sizeof(int) * nprob));
   CKM(cudaMalloc(&m->iters, sizeof(int) * nprob));
-  m->smem = sizeof(double) * ((size_t)m->nm * m->nm + 2 * m->nm + (size_t)(m->nm + 1) * (AND_TILE + 1) + AND_THREADS) +
-            sizeof(int) * (AND_THREADS + m->nm + 4);
-  CKM(cudaFuncSetAttribute((const void *)anderson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+  auto smem_for = [](size_t nm) {
+    return sizeof(double) * (nm * nm + 2 * nm + (nm + 1) * (AND_TILE + 1) + AND_THREADS) + sizeof(int) * (AND_THREADS + nm + 4);
+  };
+  m->smem = smem_for((size_t)m->nm);
+  // the limit is a property of the kernel, shared by every mixer of the process (other windows, other host threads):
+  // always set it to the requirement of the largest window, never to this mixer's own
+  CKM(cudaFuncSetAttribute((const void *)anderson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem_for((size_t)AND_NN_MAX)));
   *out = m;
   return SCFTB_OK;
 }
@@ -327,7 +336,8 @@ int scftb_mixer_status(scftb_mixer *m, void *stream, int *done, int *iters, doub
   return SCFTB_OK;
 }
 
-// current fields: the converged X[k] of finished problems, the latest iterate X[k] of the others
+// current fields: the converged X[k] of finished problems, the field whose residual first went NaN for done == 2,
+// the latest iterate X[k] of the others
 int scftb_mixer_get_x(scftb_mixer *m, void *stream, double *x) {
   if (!m || !x) return fail(SCFTB_ERR_ARG, "mixer: null argument");
   scftb_engine *e = m->e;
@@ -339,7 +349,18 @@ int scftb_mixer_get_x(scftb_mixer *m, void *stream, double *x) {
   CK(cudaMemcpy2D(x, sizeof(double) * n, m->X + (size_t)(m->k % m->R) * n, sizeof(double) * m->R * n, sizeof(double) * n,
                   m->nprob, cudaMemcpyDeviceToHost));
   for (int p = 0; p < m->nprob; p++)
-    if (done[p] == 1) CK(cudaMemcpy(x + (size_t)p * n, m->xfinal + (size_t)p * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (done[p] != 0) CK(cudaMemcpy(x + (size_t)p * n, m->xfinal + (size_t)p * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return SCFTB_OK;
+}
+
+int scftb_mixer_get_y(scftb_mixer *m, void *stream, int k, double *y) {
+  if (!m || !y) return fail(SCFTB_ERR_ARG, "mixer: null argument");
+  if (k < 0 || k >= m->k || k < m->k - m->R) return fail(SCFTB_ERR_STATE, "mixer: residual of that iteration is not in the ring");
+  const size_t n = m->e->ni;
+  CK(cudaSetDevice(m->e->cfg.device));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  CK(cudaMemcpy2D(y, sizeof(double) * n, m->Y + (size_t)(k % m->R) * n, sizeof(double) * m->R * n, sizeof(double) * n,
+                  m->nprob, cudaMemcpyDeviceToHost));
   return SCFTB_OK;
 }
 

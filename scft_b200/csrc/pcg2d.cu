@@ -630,7 +630,8 @@ struct scftb2d_engine {
   std::vector<void *> opened;
   double **d_peers;
   unsigned long long seq, rseq;
-  volatile long long *h_dbg;
+  volatile long long *h_dbg = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 #define NK(call)                                                                                              \
@@ -657,6 +658,8 @@ int scftb2d_destroy(scftb2d_engine *e) {
   for (auto &a : g_arenas) if (a.base == e->d_xchg) a.busy = false;
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->h_flag) cudaFreeHost(e->h_flag);
+  if (e->h_dbg) cudaFreeHost((void *)e->h_dbg);
+  if (e->ev0) { cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); }
   if (e->comm) g_nccl.CommDestroy(e->comm);
   for (void *p : {(void *)e->M.S.col, (void *)e->M.S.valT, (void *)e->M.S.valA, (void *)e->M.S.dinv, (void *)e->d_eta,
                   (void *)e->d_peers, (void *)e->M.V.x, (void *)e->M.V.r, (void *)e->M.V.s, (void *)e->M.V.p,
@@ -725,7 +728,15 @@ int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_en
     e->p2p.rank = cfg->rank; e->p2p.world = cfg->world; e->p2p.peers = nullptr;
     const int lx0 = cfg->rank > 0 ? (int)((long long)(nx + 1) * (cfg->rank - 1) / cfg->world) : 0;
     e->p2p.nrows_left = cfg->rank > 0 ? (e->ix0 - lx0) * nyp : 0;
-    e->p2p.timeout = 6000000000LL;   // ~3 s of SM clocks
+    // bound on a peer-flag wait, in SM clocks (~2 GHz).  Ranks can be skewed by seconds at the first launch (module load,
+    // host paging, a large eta upload on one rank), so the default is a minute, not a few launch latencies;
+    // SCFTB_P2P_TIMEOUT_S overrides it.  Expiry still __trap()s (a peer that never arrives would otherwise hang the GPU).
+    {
+      const char *ts = getenv("SCFTB_P2P_TIMEOUT_S");
+      double sec = ts ? atof(ts) : 60.0;
+      if (!(sec > 0.0)) sec = 60.0;
+      e->p2p.timeout = (long long)(sec * 2.0e9);
+    }
     CK2(cudaHostAlloc((void **)&e->h_dbg, sizeof(long long) * 8, cudaHostAllocMapped));
     memset((void *)e->h_dbg, 0, sizeof(long long) * 8);
     long long *ddbg = nullptr;
@@ -846,8 +857,8 @@ int scftb2d_residual(scftb2d_engine *e, const double *eta, double *out) {
   CK(cudaMemcpyAsync(e->d_eta, eta, sizeof(double) * e->ndof, cudaMemcpyHostToDevice, st));
   assemble2d_kernel<<<(e->nslices * 32 + 255) / 256, 256, 0, st>>>(e->M.S);
   g_launches++;
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  if (!e->ev0) { CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1)); }   // owned by the engine: no leak on error returns
+  cudaEvent_t e0 = e->ev0, e1 = e->ev1;
   CK(cudaEventRecord(e0, st));
   March2D M = e->M;
   if (e->cfg.world > 1 && e->attached) {
@@ -920,7 +931,6 @@ int scftb2d_residual(scftb2d_engine *e, const double *eta, double *out) {
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e0, e1));
   e->last_ms = ms;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   CK(cudaMemcpy(&e->last_iters, M.iters, sizeof(long long), cudaMemcpyDeviceToHost));
   std::vector<double> phi(e->nrows);
   CK(cudaMemcpy(phi.data(), M.phi, sizeof(double) * e->nrows, cudaMemcpyDeviceToHost));

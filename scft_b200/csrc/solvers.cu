@@ -20,7 +20,9 @@
 
 using namespace scftb;
 
-static scftb_engine *g_bound = nullptr;
+// the engine behind the reference-shaped callbacks, the role of the global `heat_equation_solver` (drivescft.cc:50).
+// Per host thread: threads that drive their own engines (sweeps) each bind their own.
+static thread_local scftb_engine *g_bound = nullptr;
 extern "C" int scftb_funcerr = 0;
 
 namespace scftb {
@@ -286,7 +288,7 @@ struct BroydenState {  // what the reference keeps in caller-owned globals qt, r
   int n = 0;
   std::vector<double> qt, r, d;
 };
-BroydenState g_broyden;
+thread_local BroydenState g_broyden;   // per host thread, like the binding above
 
 }  // namespace
 
@@ -341,7 +343,9 @@ extern "C" int scftb_broydn(scftb_func vecfunc, double *x, int n, int *check, do
         int B = scftb_engine_max_batch(g_bound);
         for (int j0 = 0; j0 < n && batched; j0 += B) {
           int nb = std::min(B, n - j0);
-          if (scftb_residual_batch(g_bound, nb, &xb[(size_t)j0 * n], &fb[(size_t)j0 * n]) != SCFTB_OK) { scftb_funcerr = 1; }
+          // every column with the parameters of problem 0 (the problem the callback evaluates), whatever (tau, L, mesh)
+          // the other slots of a sweep engine hold; their phi/Q/eta_full are left untouched
+          if (residual_batch_shared(g_bound, nb, &xb[(size_t)j0 * n], &fb[(size_t)j0 * n]) != SCFTB_OK) { scftb_funcerr = 1; }
         }
       }
       if (vecfunc == scftb_callback_ab_c0 && g_bound) {   // two-species: the 2(N-2) columns in device batches
@@ -349,7 +353,7 @@ extern "C" int scftb_broydn(scftb_func vecfunc, double *x, int n, int *check, do
         int B = scftb_engine_max_batch(g_bound);
         for (int j0 = 0; j0 < n && batched; j0 += B) {
           int nb = std::min(B, n - j0);
-          if (scftb_residual_ab_batch(g_bound, nb, &xb[(size_t)j0 * n], &fb[(size_t)j0 * n]) != SCFTB_OK) { scftb_funcerr = 1; }
+          if (residual_ab_batch_shared(g_bound, nb, &xb[(size_t)j0 * n], &fb[(size_t)j0 * n]) != SCFTB_OK) { scftb_funcerr = 1; }
         }
       }
       if (!batched)

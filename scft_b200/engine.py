@@ -47,7 +47,7 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_broydn_device", "scftb_broydn_device_ex", "scftb_adm_chen_batch",
            "scftb_set_diblock", "scftb_residual_ab", "scftb_residual_ab_batch", "scftb_get_phi_ab", "scftb_callback_ab_c0",
            "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
-           "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_refine_mesh_adaptive", "scftb_write_solution",
+           "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_get_y", "scftb_get_slots", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_refine_mesh_adaptive", "scftb_write_solution",
            "scftb_read_solution", "scftb_read_res", "scftb2d_nccl_unique_id", "scftb2d_create", "scftb2d_destroy",
            "scftb2d_rows", "scftb2d_p2p_handle", "scftb2d_p2p_attach", "scftb2d_p2p_detach", "scftb2d_residual", "scftb2d_get_phi", "scftb2d_get_stats", "scftb2d_export_csr"]
 
@@ -94,6 +94,8 @@ def lib():
         L.scftb_mixer_set_freeze.argtypes = [C.c_void_p, C.c_int]
         L.scftb_mixer_status.argtypes = [C.c_void_p, C.c_void_p, _ip, _ip, _dp]
         L.scftb_mixer_get_x.argtypes = [C.c_void_p, C.c_void_p, _dp]
+        L.scftb_mixer_get_y.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp]
+        L.scftb_get_slots.argtypes = [C.c_void_p, _ip]
         L.scftb_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.scftb_get_march_ms.argtypes = [C.c_void_p, _dp, _ip]
         L.scftb_spline.argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double]
@@ -174,6 +176,12 @@ class Engine:
         tot, cnt = C.c_double(0), C.c_int(0)
         _chk(lib().scftb_get_march_ms(self._h, C.byref(tot), C.byref(cnt)))
         return tot.value, cnt.value
+
+    def slots(self):
+        """resident CTA slots of the march kernel (problems per wave)"""
+        v = C.c_int(0)
+        _chk(lib().scftb_get_slots(self._h, C.byref(v)))
+        return v.value
 
     def residual_device(self, nprob, d_eta_ptr, d_out_ptr, stream_ptr=0):
         _chk(lib().scftb_residual_batch_device(self._h, nprob, C.c_void_p(d_eta_ptr), C.c_void_p(d_out_ptr),
@@ -287,6 +295,12 @@ class AndersonBatch:
     def x(self, stream_ptr=0):
         out = np.zeros((self.nprob, self.eng.ni))
         _chk(lib().scftb_mixer_get_x(self._h, C.c_void_p(stream_ptr), _p(out)))
+        return out
+
+    def y(self, stream_ptr, k):
+        """residuals F(X_k) of iteration k"""
+        out = np.zeros((self.nprob, self.eng.ni))
+        _chk(lib().scftb_mixer_get_y(self._h, C.c_void_p(stream_ptr), k, _p(out)))
         return out
 
 
