@@ -14,6 +14,7 @@
 
 #include "march1d.cuh"
 #include "march_irk4.cuh"
+#include "march1d_tmem.cuh"
 
 namespace scftb {
 
@@ -152,7 +153,15 @@ int choose_kernel(int ni, bool uni, KernelChoice &kc, bool odd) {
   if (C == 16 && T == 128) kc.fn = pick<16, 128, 1>(uni, odd);
   if (C == 16 && T == 256) kc.fn = pick<16, 256, 1>(uni, odd);
   if (!kc.fn) return 1;
-  kc.C = C; kc.T = T;
+  kc.C = C; kc.T = T; kc.dyn_smem = 0; kc.max_occ = 0;
+  // the benchmarked shape (513..1024 unknowns on a uniform mesh, even step count): coefficients in tensor memory,
+  // <= 128 registers, four CTAs per SM.  SCFTB_NO_TMEM=1 keeps the register-resident kernel (A/B measurements).
+  const char *no_tm = getenv("SCFTB_NO_TMEM");
+  if (C == 8 && T == 128 && uni && !odd && !(no_tm && atoi(no_tm))) {
+    kc.fn = (march_fn)march_tm_kernel;
+    kc.dyn_smem = 30 * 1024;   // static + dynamic > 228 KB / 5: a fifth CTA (no tensor-memory columns left) never lands
+    kc.max_occ = 4;
+  }
   return 0;
 }
 
@@ -177,7 +186,7 @@ int choose_kernel_irk4(int ni, bool uni, KernelChoice &kc) {
   if (C == 4 && T == 256) kc.fn = pick4<4, 256>(uni);
   if (C == 8 && T == 256) kc.fn = pick4<8, 256>(uni);
   if (!kc.fn) return 1;
-  kc.C = C; kc.T = T;
+  kc.C = C; kc.T = T; kc.dyn_smem = 0; kc.max_occ = 0;
   return 0;
 }
 
@@ -265,8 +274,21 @@ int scftb_create(const scftb_config *cfg, scftb_engine **out) {
   e->SL = (size_t)e->kc.T * e->kc.C;
   int sms = 0, occ = 0;
   CKD(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-  CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)e->kc.fn, e->kc.T, 0));
+  if (e->kc.dyn_smem) {
+    CKD(cudaFuncSetAttribute((const void *)e->kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->kc.dyn_smem));
+    // four CTAs of ~50 KB each need most of the SM's unified L1/shared array configured as shared memory
+    CKD(cudaFuncSetAttribute((const void *)e->kc.fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int)cudaSharedmemCarveoutMaxShared));
+  }
+  CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)e->kc.fn, e->kc.T, e->kc.dyn_smem));
   if (occ < 1) occ = 1;
+  // The occupancy query answers 1 for any kernel that allocates tensor memory (CUDA 12.9), but the hardware does keep
+  // four such CTAs resident when registers, shared memory and TMEM columns allow it (measured: 592 CTAs of this kernel
+  // run as ONE wave, tools/lat2.py).  The slot count only has to be an upper bound on resident CTAs (history buffers are
+  // indexed by blockIdx.x), so the designed value is used.
+  if (e->kc.max_occ) occ = e->kc.max_occ;
+  if (getenv("SCFTB_FORCE_OCC")) occ = atoi(getenv("SCFTB_FORCE_OCC"));   // experiments: resident-CTA slots per SM
+  if (getenv("SCFTB_DEBUG")) fprintf(stderr, "scftb: march kernel C=%d T=%d dyn_smem=%d occupancy=%d CTAs/SM\n", e->kc.C, e->kc.T, e->kc.dyn_smem, occ);
   e->slots = std::min(B, sms * occ);
   e->nslices = cfg->store_history ? n + 1 : n / 2 + 1;
   size_t nh = (size_t)(cfg->store_history ? B : e->slots) * e->nslices * e->SL;
@@ -403,7 +425,7 @@ int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_
     else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
     CK(cudaEventRecord(ev.first, st));
   }
-  e->kc.fn<<<grid, e->kc.T, 0, st>>>(P);
+  e->kc.fn<<<grid, e->kc.T, e->kc.dyn_smem, st>>>(P);
   if (e->timing) { CK(cudaEventRecord(ev.second, st)); e->ev_pending.push_back(ev); }
   g_launches++;
   CK(cudaGetLastError());

@@ -23,6 +23,8 @@ typedef void (*march_fn)(MarchParams);
 struct KernelChoice {
   int C, T;
   march_fn fn;
+  int dyn_smem = 0;   // dynamic shared memory per CTA (the tensor-memory kernel pads itself to four CTAs per SM)
+  int max_occ = 0;    // cap on resident CTAs per SM (0: whatever the occupancy query says)
 };
 extern std::atomic<long> g_launches;
 int choose_kernel(int ni, bool uni, KernelChoice &kc, bool odd);
