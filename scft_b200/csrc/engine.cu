@@ -159,7 +159,7 @@ int choose_kernel(int ni, bool uni, KernelChoice &kc, bool odd) {
   const char *no_tm = getenv("SCFTB_NO_TMEM");
   if (C == 8 && T == 128 && uni && !odd && !(no_tm && atoi(no_tm))) {
     kc.fn = (march_fn)march_tm_kernel;
-    kc.dyn_smem = 30 * 1024;   // static + dynamic > 228 KB / 5: a fifth CTA (no tensor-memory columns left) never lands
+    kc.dyn_smem = 12 * 1024;   // static + dynamic > 228 KB / 5: a fifth CTA (no tensor-memory columns left) never lands
     kc.max_occ = 4;
   }
   return 0;

@@ -24,6 +24,15 @@
 
 namespace scftb {
 
+#ifndef TM_TWOSIDED
+// 1: two-sided chunk elimination (dependent chain per step 8 instead of 13 operations; single-CTA latency 989 -> 848
+// cycles per step) — measured NOT to raise the throughput at four CTAs per SM (1740 vs 1673 cycles per four steps: its
+// extra temporaries spill), so the one-sided UL sweeps stay the default
+#define TM_TWOSIDED 0
+#endif
+#ifndef TM_PREFETCH
+#define TM_PREFETCH 2   // contour steps the paired history slice is fetched ahead (ring of 4 staging buffers)
+#endif
 constexpr int TM_COLS = 128;
 constexpr int TM_A = 0, TM_B = 16, TM_C = 48, TM_D = 80;
 
@@ -84,7 +93,11 @@ __global__ void __launch_bounds__(128, 4) march_tm_kernel(MarchParams P) {
   __shared__ __align__(16) double s_minv[NW][NW];    // inverse of the level-3 matrix
   __shared__ __align__(16) double s_pub[2][NW][2];   // per step: {A_v, B_{v+1}} -> R_v = A_v + B_{v+1} (double-buffered)
   __shared__ double s_red[NW];
-  __shared__ __align__(16) double s_qo[2][C / 2][T][2];   // staging ring for the paired history slice q(., n-j)
+  // staging ring for the paired history slices q(., n-j): fetched PD steps ahead, so that PD slices per CTA (x 4 CTAs per
+  // SM) are in flight — one slice per CTA is not enough memory-level parallelism to cover the loaded HBM latency
+  constexpr int RING = 4, PD = TM_PREFETCH;
+  static_assert(PD >= 1 && PD < RING, "prefetch distance");
+  __shared__ __align__(16) double s_qo[RING][C / 2][T][2];
   __shared__ uint32_t s_tm;
   // keep at most four CTAs on an SM whatever the register count turns out to be: the fifth could not allocate its
   // tensor-memory columns (4 x 128 = all 512) and would spin in tcgen05.alloc
@@ -112,6 +125,51 @@ __global__ void __launch_bounds__(128, 4) march_tm_kernel(MarchParams P) {
         sl = rs.Tl; sd = rs.Td; su = rs.Tu;
         sAd = (rs.Al != 0.0) ? rs.Al : rs.Au;    // A_off; Dirichlet zeroing is carried by the neighbour values
       }
+#if TM_TWOSIDED
+      // Two-sided ("burn at both ends") elimination of the chunk: nodes 0..2 are eliminated downwards, nodes 6..4 upwards,
+      // both meet at node 3, and the substitution runs outwards from there.  Same operation count as the one-sided sweeps,
+      // but the dependent chain per contour step is 2 + 2 + 1 + 3 operations instead of 6 + 1 + 6.
+      //   al[] <- the six elimination multipliers  m1, m2, m4, m5, mL3, mR3        (block A)
+      //   ca[] <- A_off / pivot_k  (k = 0..6; node 3 goes to block A)               (block B)
+      //   be[] <- substitution couplings d0, d1, d2 (to node k+1), d4, d5, d6 (to node k-1), be[0] unused
+      {
+        Row rw[CI];
+        double piv[CI];
+#pragma unroll
+        for (int k = 0; k < CI; k++) rw[k] = assemble_row(P, p, t * C + k, L, dt);
+        double mL[CI], mR[CI];   // multipliers applied to the upper / lower neighbour's row
+        piv[0] = rw[0].Td;
+#pragma unroll
+        for (int k = 1; k <= 2; k++) { mL[k] = rw[k].Tl / piv[k - 1]; piv[k] = rw[k].Td - mL[k] * rw[k - 1].Tu; }
+        piv[6] = rw[6].Td;
+#pragma unroll
+        for (int k = 5; k >= 4; k--) { mR[k] = rw[k].Tu / piv[k + 1]; piv[k] = rw[k].Td - mR[k] * rw[k + 1].Tl; }
+        mL[3] = rw[3].Tl / piv[2]; mR[3] = rw[3].Tu / piv[4];
+        piv[3] = rw[3].Td - mL[3] * rw[2].Tu - mR[3] * rw[4].Tl;
+        auto solve = [&](const double (&rhs)[CI], double (&x)[CI]) {   // exact chunk solve with these factors
+          double y[CI];
+          y[0] = rhs[0]; y[1] = rhs[1] - mL[1] * y[0]; y[2] = rhs[2] - mL[2] * y[1];
+          y[6] = rhs[6]; y[5] = rhs[5] - mR[5] * y[6]; y[4] = rhs[4] - mR[4] * y[5];
+          y[3] = rhs[3] - mL[3] * y[2] - mR[3] * y[4];
+          x[3] = y[3] / piv[3];
+          x[2] = (y[2] - rw[2].Tu * x[3]) / piv[2]; x[1] = (y[1] - rw[1].Tu * x[2]) / piv[1]; x[0] = (y[0] - rw[0].Tu * x[1]) / piv[0];
+          x[4] = (y[4] - rw[4].Tl * x[3]) / piv[4]; x[5] = (y[5] - rw[5].Tl * x[4]) / piv[5]; x[6] = (y[6] - rw[6].Tl * x[5]) / piv[6];
+        };
+        {   // spikes: T_loc gl = Tl_first e_first, T_loc gr = Tu_last e_last
+          double e[CI] = {rw[0].Tl, 0, 0, 0, 0, 0, 0};
+          solve(e, gl);
+          double f[CI] = {0, 0, 0, 0, 0, 0, rw[6].Tu};
+          solve(f, gr);
+        }
+        al[0] = mL[1]; al[1] = mL[2]; al[2] = mR[4]; al[3] = mR[5]; al[4] = mL[3]; al[5] = mR[3]; al[6] = 0.0;
+#pragma unroll
+        for (int k = 0; k < CI; k++) {
+          const double aoff = (rw[k].Al == 0.0) ? rw[k].Au : rw[k].Al;
+          ca[k] = aoff / piv[k];
+          be[k] = (k < 3) ? rw[k].Tu / piv[k] : ((k > 3) ? rw[k].Tl / piv[k] : 0.0);
+        }
+      }
+#else
       {
         double Tl0 = 0, TuL = 0, pinv_next = 0, Tl_next = 0;
         double ulo[CI];
@@ -139,8 +197,22 @@ __global__ void __launch_bounds__(128, 4) march_tm_kernel(MarchParams P) {
 #pragma unroll
         for (int k = 1; k < CI; k++) gr[k] = y[k] - be[k] * gr[k - 1];
       }
+#endif
       {   // blocks A, B and the spikes of block D are final: park them in tensor memory
         uint32_t w16[16];
+#if TM_TWOSIDED
+        // block A: m1, m2, m4, m5, mL3, mR3, c3, sl     block B: c0,c1,c2,c4,c5,c6, d0,d1,d2,d4,d5,d6, A_off, su
+#pragma unroll
+        for (int k = 0; k < 6; k++) tm_put(w16, k, al[k]);
+        tm_put(w16, 6, ca[3]); tm_put(w16, 7, sl);
+        tm_st16(tb + TM_A, w16);
+        tm_put(w16, 0, ca[0]); tm_put(w16, 1, ca[1]); tm_put(w16, 2, ca[2]); tm_put(w16, 3, ca[4]); tm_put(w16, 4, ca[5]); tm_put(w16, 5, ca[6]);
+        tm_put(w16, 6, be[0]); tm_put(w16, 7, be[1]);
+        tm_st16(tb + TM_B, w16);
+        tm_put(w16, 0, be[2]); tm_put(w16, 1, be[4]); tm_put(w16, 2, be[5]); tm_put(w16, 3, be[6]);
+        tm_put(w16, 4, sAd); tm_put(w16, 5, su); tm_put(w16, 6, 0.0); tm_put(w16, 7, 0.0);
+        tm_st16(tb + TM_B + 16, w16);
+#else
 #pragma unroll
         for (int k = 0; k < 6; k++) tm_put(w16, k, al[k]);
         tm_put(w16, 6, ca[0]); tm_put(w16, 7, sl);
@@ -153,6 +225,7 @@ __global__ void __launch_bounds__(128, 4) march_tm_kernel(MarchParams P) {
         for (int k = 0; k < 4; k++) tm_put(w16, k, be[k + 3]);
         tm_put(w16, 4, sAd); tm_put(w16, 5, su); tm_put(w16, 6, 0.0); tm_put(w16, 7, 0.0);
         tm_st16(tb + TM_B + 16, w16);
+#endif
 #pragma unroll
         for (int k = 0; k < 7; k++) tm_put(w16, k, gl[k]);
         tm_put(w16, 7, gr[0]);
@@ -309,19 +382,47 @@ __global__ void __launch_bounds__(128, 4) march_tm_kernel(MarchParams P) {
     auto step = [&](auto ph, const int j) {
       constexpr int PH = decltype(ph)::value;
       hw += SL; hr -= SL;
-      if (PH >= 1) {   // the slice the NEXT step pairs with is fetched a whole step ahead
-        if (j < n) {
-          const unsigned dst = qo_me + ((j + 1) & 1) * QO_BUF;
-          const double *src = hr - SL;
+      if (PH >= 1) {   // the slices the next PD steps pair with are in flight; fetch the one for step j + PD
 #pragma unroll
-          for (int k = 0; k < C; k += 2) cp_async16(dst + (k / 2) * T * 16, src + k * T);
+        for (int a = (PH == 1 ? 1 : PD); a <= PD; a++) {   // the middle step starts the pipeline: steps j+1 .. j+PD
+          if (j + a <= n) {
+            const unsigned dst = qo_me + ((j + a) & (RING - 1)) * QO_BUF;
+            const double *src = hr - a * SL;
+#pragma unroll
+            for (int k = 0; k < C; k += 2) cp_async16(dst + (k / 2) * T * 16, src + k * T);
+          }
+          cp_async_commit();
         }
-        cp_async_commit();
       }
       double wj = 0.0;
       if (PH >= 1) wj = __ldg(wq + j);
       uint32_t rB[32];
       tm_ld32(tb + TM_B, rB);
+#if TM_TWOSIDED
+      // ---- eliminations from both chunk ends towards node 3 (block A), on u = b / A_off
+      double z[CI];
+      {
+        double tk[CI];
+#pragma unroll
+        for (int k = 0; k < CI; k++) tk[k] = fma(4.0, q[k], ((k == 0) ? XL : q[k - 1]) + q[k + 1]);
+        const double y1 = fma(-tm_get(rA, 0), tk[0], tk[1]), y5 = fma(-tm_get(rA, 3), tk[6], tk[5]);
+        const double y2 = fma(-tm_get(rA, 1), y1, tk[2]), y4 = fma(-tm_get(rA, 2), y5, tk[4]);
+        const double y3 = fma(-tm_get(rA, 4), y2, fma(-tm_get(rA, 5), y4, tk[3]));
+        z[3] = tm_get(rA, 6) * y3;
+        z[0] = tk[0]; z[1] = y1; z[2] = y2; z[4] = y4; z[5] = y5; z[6] = tk[6];
+      }
+      const double sl = tm_get(rA, 7);
+      // ---- substitution outwards from node 3 and separator row (block B)
+      tm_wait_ld();
+      tm_pin(rB);
+      z[2] = fma(-tm_get(rB, 8), z[3], tm_get(rB, 2) * z[2]);
+      z[4] = fma(-tm_get(rB, 9), z[3], tm_get(rB, 3) * z[4]);
+      z[1] = fma(-tm_get(rB, 7), z[2], tm_get(rB, 1) * z[1]);
+      z[5] = fma(-tm_get(rB, 10), z[4], tm_get(rB, 4) * z[5]);
+      z[0] = fma(-tm_get(rB, 6), z[1], tm_get(rB, 0) * z[0]);
+      z[6] = fma(-tm_get(rB, 11), z[5], tm_get(rB, 5) * z[6]);
+      const double zfn = shfl_dn_d(z[0], 1);
+#else
       // ---- first sweep (block A): u = b / A_off from the right end of the chunk
       double z[CI];
 #pragma unroll
@@ -338,6 +439,7 @@ __global__ void __launch_bounds__(128, 4) march_tm_kernel(MarchParams P) {
       tm_pin(rB);
 #pragma unroll
       for (int k = 1; k < CI; k++) z[k] = fma(-tm_get(rB, 5 + k), z[k - 1], tm_get(rB, k - 1) * z[k]);
+#endif
       const double Aoff = tm_get(rB, 12), su = tm_get(rB, 13);
       uint32_t rC[32];
       tm_ld32(tb + TM_C, rC);
@@ -404,8 +506,8 @@ __global__ void __launch_bounds__(128, 4) march_tm_kernel(MarchParams P) {
         for (int k = 0; k < C; k++) phi[k] = fma(wj * q[k], q[k], phi[k]);
       }
       if (PH == 2) {
-        cp_async_wait1();
-        const unsigned src = qo_me + (j & 1) * QO_BUF;
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(PD) : "memory");   // all but the PD newest groups have landed
+        const unsigned src = qo_me + (j & (RING - 1)) * QO_BUF;
 #pragma unroll
         for (int k = 0; k < C; k += 2) {
           const double2 v = lds128(src + (k / 2) * T * 16);
@@ -414,10 +516,14 @@ __global__ void __launch_bounds__(128, 4) march_tm_kernel(MarchParams P) {
         }
       }
     };
+    // two steps per loop trip: the second step's sweeps do not depend on the first step's history store / quadrature
+    // update, so the scheduler can slide those under the dependent chains of the next step
     int j = 1;
+    for (; 2 * (j + 1) < n; j += 2) { step(std::integral_constant<int, 0>{}, j); step(std::integral_constant<int, 0>{}, j + 1); }
     for (; 2 * j < n; j++) step(std::integral_constant<int, 0>{}, j);
     step(std::integral_constant<int, 1>{}, j);   // n is even: j = n/2
-    for (j++; j <= n; j++) step(std::integral_constant<int, 2>{}, j);
+    for (j++; j + 1 <= n; j += 2) { step(std::integral_constant<int, 2>{}, j); step(std::integral_constant<int, 2>{}, j + 1); }
+    for (; j <= n; j++) step(std::integral_constant<int, 2>{}, j);
     cp_async_wait0();
 
     // ------------------------------------------------------------------ residual, phi, Q

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libscft_b200.so")
+# SCFTB_LIB: another build of the same library (kernel-variant experiments, tools/build_variant.sh)
+LIB_PATH = os.environ.get("SCFTB_LIB") or os.path.join(HERE, "lib", "libscft_b200.so")
 
 IE_ROWSCALE, IE_CONSISTENT, IRK4_CONSISTENT = 0, 1, 2
 QUAD_ROMBERG, QUAD_TRAPEZOID = 0, 1
