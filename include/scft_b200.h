@@ -160,12 +160,20 @@ void scftb_callback_ab_c0(int n, double *in, double *out);
 int scftb_adm_chen_batch(scftb_engine *e, int nprob, double *x, double tol, int maxIteration,
                          double lmd, int nn, int Final, int *iters_out, double *err_out);
 
+/* adm (adm.c:24-313) for a batch, device-resident: the fixed-point map is x -> x + (phi0 - phi)
+ * (scftb_callback_fixedpoint_c0), history ring of NRMAX = 10 (adm.c:6), lambda = 0.05 then 1 - 0.95^its (adm.c:140,151),
+ * gaussj with the zero-pivot nudge of the root gaussj.c:38, TOLF = 1e-10 (adm.c:29).  Bit-identical to scftb_adm driven by
+ * scftb_callback_fixedpoint_c0.  At most maxits evaluations per problem; 0 when every problem converged. */
+int scftb_adm_batch(scftb_engine *e, int nprob, double *x, int maxits, int *iters_out, double *err_out);
+
 /* The same, one iteration at a time, for callers that keep the fields on the device (sweeps,
  * benchmarks).  A mixer owns the per-problem history rings X,Y (ADM_chen_C.c:49-50), lk and the
  * restart index.  scftb_mixer_iterate_device issues Y_k = F(X_k) and the Anderson update on the
  * caller's stream and returns immediately; converged problems are frozen and skipped. */
 typedef struct scftb_mixer scftb_mixer;
 int scftb_mixer_create(scftb_engine *e, int nprob, double tol, double lmd, int nn, int Final, scftb_mixer **out);
+/* adm semantics instead of adm_chen (see scftb_adm_batch); all other mixer calls apply unchanged */
+int scftb_adm_mixer_create(scftb_engine *e, int nprob, scftb_mixer **out);
 int scftb_mixer_destroy(scftb_mixer *m);
 int scftb_mixer_reset(scftb_mixer *m, const double *x, int x_is_device, void *stream);
 /* freeze = 1 (default): converged / NaN problems are skipped from then on, as adm_chen returns or
@@ -177,6 +185,54 @@ int scftb_mixer_status(scftb_mixer *m, void *stream, int *done, int *iters, doub
 int scftb_mixer_get_x(scftb_mixer *m, void *stream, double *x /* host [nprob][N-2] */);
 /* residuals Y_k = F(X_k) of iteration k (ADM_chen_C.c:50,57), still in the ring while k > iterations issued - nn - 2 */
 int scftb_mixer_get_y(scftb_mixer *m, void *stream, int k, double *y /* host [nprob][N-2] */);
+
+/* ---- preconditioned Anderson mixing and the continuation sweep solver (pmixer.cu) ------------------------------
+ * B200-first replacement of the reference's staged adm_chen schedule (drivescft.cc:294-298) for batches: the adm_chen
+ * update (ADM_chen_C.c:86-123) applied to the preconditioned residual -(I + Psi^-1 (1/2)(-Lap_h) Psi^-1)(phi0 - phi),
+ * Psi = diag(sqrt(phi)), relaxation 1; convergence is tested on the raw residual max|phi0 - phi| < tol exactly like
+ * adm_chen.  All problems iterate in lock-step on the device; done[p]: 0 running, 1 converged, 2 NaN start field. */
+typedef struct scftb_pmixer scftb_pmixer;
+int scftb_pmixer_create(scftb_engine *e, int nprob, double tol, int nn /* window, <= 16 */, double cap /* <= 0: 2.0 */,
+                        scftb_pmixer **out);
+int scftb_pmixer_destroy(scftb_pmixer *m);
+int scftb_pmixer_reset(scftb_pmixer *m, const double *x, int x_is_device, void *stream);
+int scftb_pmixer_iterate_device(scftb_pmixer *m, void *stream);
+int scftb_pmixer_status(scftb_pmixer *m, void *stream, int *done, int *iters, double *err);
+/* converged problems: their field; running ones: the best iterate so far.  x [nprob][N-2], host or device */
+int scftb_pmixer_get_x(scftb_pmixer *m, void *stream, double *x, int x_is_device);
+/* adm_chen-shaped convenience call for a batch: x[nprob][N-2] host in/out; returns 0 / SCFTB_ERR_NOCONV / SCFTB_ERR_NAN */
+int scftb_padm_batch(scftb_engine *e, int nprob, double *x, double tol, int maxIteration, int nn, int *iters_out,
+                     double *err_out);
+/* refine_mesh (scft.cc:132-169) for a batch of uniform meshes on the device: d_eta[nprob][N-2] -> d_eta_new[nprob][2N-3] */
+int scftb_refine_uniform_batch_device(int nprob, int N, const double *d_L, const double *d_eta, double *d_eta_new, void *stream);
+/* c[N], f0bar with  free energy = (sum_i c_i eta_i / f0bar / L + log f0bar) / -1000  (scft.cc:404-450 with the
+ * 2^18+1-point Romberg rule of scft.cc:271-281 folded into nodal weights; f0bar as testFiBar.cc:19-50); x NULL = uniform */
+int scftb_free_energy_weights(int N, const double *x, double tau, double L, double *c, double *f0bar);
+
+/* The reference's driver flow (drivescft.cc:259-322: solve, cut every cell in x, spline transfer, solve again) for a
+ * batch of independent problems, N0 -> 2N0-1 -> ... (levels meshes), preconditioned mixing on every level, everything
+ * between the start fields and the converged fields in HBM. */
+typedef struct scftb_sweep scftb_sweep;
+typedef struct {
+  int scheme;       /* SCFTB_IE_* / SCFTB_IRK4_* */
+  int N0, levels;   /* coarsest mesh and number of meshes: target N = (N0-1) 2^(levels-1) + 1 */
+  int nsteps, quadrature;
+  double tol;       /* on max|phi0 - phi|, every level (<= 0: 1e-9) */
+  int nn;           /* mixing window (<= 0: 10) */
+  int maxit;        /* evaluations per level (<= 0: 200) */
+  double cap;       /* step cap while max|F| > 1e-2 (<= 0: 2.0) */
+  int device;
+} scftb_sweep_config;
+#define SCFTB_SWEEP_COLS 7
+int scftb_sweep_create(const scftb_sweep_config *cfg, int max_prob, scftb_sweep **out);
+int scftb_sweep_destroy(scftb_sweep *s);
+int scftb_sweep_target_N(scftb_sweep *s);
+/* tau[nprob], L[nprob], eta0[nprob][N0-2] (host) -> eta_out[nprob][N_target-2] (host, may be NULL) and
+ * rows[nprob][SCFTB_SWEEP_COLS] = { status (0 converged on every level / 1 not / 2 NaN), max|phi0-phi| on the last level
+ * reached, evaluations summed over the levels, Q, free energy (f0bar of the problem's own (tau, L)), evaluations on the
+ * last level, N of the last level reached }; level_seconds[levels] (may be NULL) */
+int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double *L, const double *eta0, double *eta_out,
+                      double *rows, double *level_seconds);
 
 /* ---- around the hot path: spline, refinement, result files ------------------- */
 /* spline_chen (spline_chen.c:12-106): mode 0 natural (m = 0), 1 not-a-knot (m == NULL), 2 y'' = bc at both

@@ -29,6 +29,8 @@ constexpr int AND_NN_MAX = 50;
 
 struct AndersonParams {
   int n, nprob, R, nm, k, Final, freeze;
+  int adm;             // 1: adm.c semantics (see scftb_adm_mixer_create): d = (x + F) - x, window min(k, nm), nudged gaussj, relax = lambda_k
+  double relax;        // adm: lambda of this iteration (adm.c:140,151), computed on the host with the host's pow()
   double tol, lmd;
   double *X, *Y;       // [nprob][R][n]
   double *xfinal;      // [nprob][n]
@@ -53,6 +55,12 @@ __global__ void __launch_bounds__(AND_THREADS) anderson_kernel(AndersonParams A)
 
   const double *Xp = A.X + (size_t)p * R * n, *Yp = A.Y + (size_t)p * R * n;
   const double *Yk = Yp + (size_t)(k % R) * n, *Xk = Xp + (size_t)(k % R) * n;
+
+  if (A.adm) {   // adm works on x = f(x) with f(x) = x + F(x) (drivescft.cc:212 comment): d = xnew - x = (x + F) - x, adm.c:163
+    double *Yw = A.Y + (size_t)p * R * n + (size_t)(k % R) * n;
+    for (int i = tid; i < n; i += AND_THREADS) Yw[i] = __dsub_rn(__dadd_rn(Yw[i], Xk[i]), Xk[i]);
+    __syncthreads();
+  }
 
   // ---- err = max |Y_k|, NaN check (ADM_chen_C.c:58-69)
   double e = 0.0;
@@ -86,7 +94,7 @@ __global__ void __launch_bounds__(AND_THREADS) anderson_kernel(AndersonParams A)
     return;
   }
   double lk = A.lk[p];
-  int m = min(nm, k - A.k_restart[p]);
+  int m = A.adm ? min(nm, k) : min(nm, k - A.k_restart[p]);   // adm.c:150 nr = IMIN(its-1, NRMAX), its = k+1
 
   if (m > 0) {
     // ---- U (upper triangle incl. diagonal) and V, sequential in t per entry (ADM_chen_C.c:89-101)
@@ -170,7 +178,8 @@ __global__ void __launch_bounds__(AND_THREADS) anderson_kernel(AndersonParams A)
       }
       if (tid == 0) {
         double piv = U[icol * m + icol];
-        if (piv == 0.0) s_sing = 1;               // gaussj.c:46-50
+        if (piv == 0.0 && A.adm) piv += 1e-18;    // root gaussj.c:38 (the one adm.c:278 links)
+        if (piv == 0.0) s_sing = 1;               // DEALII_SCFT/src/gaussj.c:46-50
         else { s_pivinv = 1.0 / piv; U[icol * m + icol] = 1.0; }
       }
       __syncthreads();
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(AND_THREADS) anderson_kernel(AndersonParams A)
 
   // ---- X_{k+1} (ADM_chen_C.c:114-123)
   double *Xn = A.X + (size_t)p * R * n + (size_t)((k + 1) % R) * n;
-  const double oml = 1 - lk;
+  const double oml = A.adm ? A.relax : 1 - lk;
   for (int i = tid; i < n; i += AND_THREADS) {
     const double xk = Xk[i], yk = Yk[i];
     double cx = 0.0, cd = 0.0;
@@ -210,7 +219,7 @@ __global__ void __launch_bounds__(AND_THREADS) anderson_kernel(AndersonParams A)
     }
     Xn[i] = __dadd_rn(__dadd_rn(xk, cx), __dmul_rn(oml, __dadd_rn(yk, cd)));
   }
-  if (tid == 0) {                         // ADM_chen_C.c:125-132
+  if (tid == 0 && !A.adm) {               // ADM_chen_C.c:125-132
     if (err < 0.03 && k > 100) lk *= A.lmd;
     if (!A.Final && lk < 1e-5) lk = A.lmd;
     if (A.Final && lk < 1e-15) lk = A.lmd;
@@ -224,6 +233,7 @@ using namespace scftb;
 
 struct scftb_mixer {
   scftb_engine *e;
+  int adm = 0;
   int nprob, nn, nm, R, Final, k, freeze;
   double lmd, tol;
   double *X, *Y, *xfinal, *lk, *err;
@@ -279,6 +289,16 @@ int scftb_mixer_set_freeze(scftb_mixer *m, int freeze) {
   return SCFTB_OK;
 }
 
+// adm (adm.c:24-313) as a device-resident batched mixer: history ring of NRMAX = 10 (adm.c:6), TOLF = 1e-10 (adm.c:29),
+// lambda = 0.05 then 1 - 0.95^its, gaussj with the zero-pivot nudge of the root gaussj.c:38.  The fixed-point map is
+// x -> x + (phi0 - phi) (scftb_callback_fixedpoint_c0).  Same iterate/status/get_x calls as the adm_chen mixer.
+int scftb_adm_mixer_create(scftb_engine *e, int nprob, scftb_mixer **out) {
+  int rc = scftb_mixer_create(e, nprob, 1e-10, 0.0, 10, 0, out);
+  if (rc) return rc;
+  (*out)->adm = 1;
+  return SCFTB_OK;
+}
+
 // (re)start from fields x[nprob][n]; device = 1: x is a device pointer, copied on `stream`
 int scftb_mixer_reset(scftb_mixer *m, const double *x, int device, void *stream) {
   if (!m || !x) return fail(SCFTB_ERR_ARG, "mixer: null argument");
@@ -316,6 +336,8 @@ int scftb_mixer_iterate_device(scftb_mixer *m, void *stream) {
   AndersonParams A;
   A.n = e->ni; A.nprob = m->nprob; A.R = m->R; A.nm = m->nm; A.k = m->k; A.Final = m->Final;
   A.tol = m->tol; A.lmd = m->lmd; A.freeze = m->freeze;
+  A.adm = m->adm;
+  A.relax = m->k == 0 ? 0.05 : 1.0 - std::pow(0.95, m->k + 1);   // adm.c:140 (its = 1), adm.c:151 (its = k+1)
   A.X = m->X; A.Y = m->Y; A.xfinal = m->xfinal; A.lk = m->lk; A.err = m->err;
   A.k_restart = m->k_restart; A.done = m->done; A.iters = m->iters;
   anderson_kernel<<<m->nprob, AND_THREADS, m->smem, st>>>(A);
@@ -364,12 +386,29 @@ int scftb_mixer_get_y(scftb_mixer *m, void *stream, int k, double *y) {
   return SCFTB_OK;
 }
 
+static int mixer_batch(scftb_mixer *m, scftb_engine *e, int nprob, double *x, int maxIteration, int *iters_out, double *err_out);
+
 int scftb_adm_chen_batch(scftb_engine *e, int nprob, double *x, double tol, int maxIteration, double lmd, int nn,
                          int Final, int *iters_out, double *err_out) {
   if (!e || !x || maxIteration < 0) return fail(SCFTB_ERR_ARG, "adm_chen_batch: bad argument");
   scftb_mixer *m = nullptr;
   int rc = scftb_mixer_create(e, nprob, tol, lmd, nn, Final, &m);
   if (rc) return rc;
+  return mixer_batch(m, e, nprob, x, maxIteration, iters_out, err_out);
+}
+
+// adm for a batch, everything on the device: x[nprob][N-2] host in/out; at most maxits residual evaluations per problem
+// (adm.c MAXITS); iters_out / err_out as scftb_adm_chen_batch; returns 0 when every problem reached adm's TOLF = 1e-10
+int scftb_adm_batch(scftb_engine *e, int nprob, double *x, int maxits, int *iters_out, double *err_out) {
+  if (!e || !x || maxits < 1) return fail(SCFTB_ERR_ARG, "adm_batch: bad argument");
+  scftb_mixer *m = nullptr;
+  int rc = scftb_adm_mixer_create(e, nprob, &m);
+  if (rc) return rc;
+  return mixer_batch(m, e, nprob, x, maxits - 1, iters_out, err_out);
+}
+
+static int mixer_batch(scftb_mixer *m, scftb_engine *e, int nprob, double *x, int maxIteration, int *iters_out, double *err_out) {
+  int rc;
   rc = scftb_mixer_reset(m, x, 0, nullptr);
   std::vector<int> done(nprob, 0), iters(nprob, 0);
   bool all = false, nanseen = false;

@@ -1,0 +1,668 @@
+// pmixer.cu — preconditioned Anderson mixing, batched and device-resident, and the continuation sweep solver on top.
+//
+// The reference converges the field with adm_chen on the raw residual F = phi_0 - phi (drivescft.cc:294-298): tens of
+// thousands of iterations at m = 1024, because the Jacobian dF/d eta is a smoothing (Debye-like) operator whose
+// eigenvalues fall from ~1 to ~1e-8.  Its inverse, however, is LOCAL: in the ground-state picture phi = psi^2,
+// (-d2/dx2 + eta - eps) psi = 0, so   d eta = psi^-1 (1/2)(-d2/dx2 + ...) psi^-1 dF   — a tridiagonal operator known
+// from the phi the march has just produced.  Measured on fdjac Jacobians (N = 65..513): inv(J) equals
+//     M = I + Psi^-1 (1/2)(-Lap_h) Psi^-1,      Psi = diag(sqrt(phi_i))
+// up to a smooth remainder of relative size 1e-4, and the symbol of Psi^-1 J Psi^-1 is 2/lambda_k to 4 digits for k >= 16.
+// So the SAME Anderson update as adm_chen (ADM_chen_C.c:86-123: Gram matrix of residual differences, gaussj, the
+// X_{k+1} formula) applied to the preconditioned residual  G = -M F  with relaxation (1 - lk) = beta = 1 converges in
+// 7..10 evaluations per mesh level instead of 1e4; the low modes the local model gets wrong are what the mixing
+// history corrects.  Convergence is still tested on the RAW residual max|phi_0 - phi| < tol, like the reference.
+//
+// Safeguards (only active far from the solution): while max|F| > 1e-2 the step is scaled to max|dx| <= cap; an iterate
+// whose residual is NaN or > blow x the best so far is discarded: restart from the best iterate with an empty
+// history and half the relaxation.
+//
+// One iteration = march launch (F(X_k), phi) + pmix_kernel (one CTA per problem); nothing crosses PCIe but the
+// per-problem done flags the host polls.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <map>
+#include <thread>
+#include <vector>
+
+#include "engine.h"
+
+namespace scftb {
+
+constexpr int PM_T = 256;
+constexpr int PM_EPT = 16;       // nodes per thread: n <= 4096 (the march kernels' own limit)
+constexpr int PM_NN_MAX = 16;
+constexpr int PM_NW = PM_T / 32;
+
+struct PMixParams {
+  int n, N, nprob, R, nm, k;
+  double tol, cap, blow, sign;
+  const double *F;      // [nprob][n] raw residual sign*(phi0 - phi) of X_k (engine d_out)
+  const double *phi;    // [nprob][N] density of X_k (engine d_phi)
+  const double *L;      // [nprob]
+  const double *xnode;  // [nprob][N] node coordinates or nullptr (uniform)
+  double *X, *G;        // rings [nprob][R][n]: iterates and preconditioned residuals
+  double *xbest, *xfinal;
+  double *beta, *best, *err;
+  int *k_restart, *done, *iters;
+};
+
+__device__ __forceinline__ double pm_wsum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+__global__ void __launch_bounds__(PM_T) pmix_kernel(PMixParams A) {
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (A.done[p]) return;
+  const int n = A.n, R = A.R, k = A.k;
+  __shared__ double s_red[PM_NW];
+  __shared__ int s_bad[PM_NW];
+  __shared__ double s_U[PM_NN_MAX * PM_NN_MAX], s_V[PM_NN_MAX];
+  __shared__ double s_scalar[3];
+  __shared__ int s_m, s_kr;
+  if (tid == 0) { s_scalar[1] = A.best[p]; s_scalar[2] = A.beta[p]; s_kr = A.k_restart[p]; }   // read once, before anyone writes them
+
+  const double *Fp = A.F + (size_t)p * n;
+  double *Xp = A.X + (size_t)p * R * n, *Gp = A.G + (size_t)p * R * n;
+  double *Xk = Xp + (size_t)(k % R) * n, *Gk = Gp + (size_t)(k % R) * n;
+
+  // ---- max|F|, NaN/Inf scan
+  double e = 0.0;
+  int bad = 0;
+  for (int i = tid; i < n; i += PM_T) {
+    const double y = Fp[i];
+    if (!isfinite(y)) bad = 1; else e = fmax(e, fabs(y));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { e = fmax(e, __shfl_xor_sync(0xffffffffu, e, d)); bad |= __shfl_xor_sync(0xffffffffu, bad, d); }
+  if (lane == 0) { s_red[wid] = e; s_bad[wid] = bad; }
+  __syncthreads();
+  e = 0.0; bad = 0;
+  for (int w = 0; w < PM_NW; w++) { e = fmax(e, s_red[w]); bad |= s_bad[w]; }
+  __syncthreads();
+  if (tid == 0) A.err[p] = bad ? nan("") : e;
+
+  if (!bad && e < A.tol) {   // converged on the raw residual (ADM_chen_C.c:71-84)
+    for (int i = tid; i < n; i += PM_T) A.xfinal[(size_t)p * n + i] = Xk[i];
+    if (tid == 0) { A.done[p] = 1; A.iters[p] = k; }
+    return;
+  }
+  const double best = s_scalar[1], beta = s_scalar[2];   // staged before the barriers of the reduction above
+  double *Xn = Xp + (size_t)((k + 1) % R) * n;
+  if (bad || (e > A.blow * best && e > 1e-2)) {
+    if (!(best < INFINITY)) {   // nothing to fall back to: the start field itself has no finite residual
+      for (int i = tid; i < n; i += PM_T) A.xfinal[(size_t)p * n + i] = Xk[i];
+      if (tid == 0) { A.done[p] = 2; A.iters[p] = k; }
+      return;
+    }
+    for (int i = tid; i < n; i += PM_T) Xn[i] = A.xbest[(size_t)p * n + i];
+    if (tid == 0) { A.beta[p] = fmax(0.5 * beta, 0.125); A.best[p] = INFINITY; A.k_restart[p] = k + 1; }
+    return;
+  }
+  if (e < best) {
+    for (int i = tid; i < n; i += PM_T) A.xbest[(size_t)p * n + i] = Xk[i];
+    if (tid == 0) A.best[p] = e;
+  }
+
+  // ---- G_k = -(F + Psi^-1 (1/2)(-Lap_h) Psi^-1 F), F = phi0 - phi
+  const double *ph = A.phi + (size_t)p * A.N;
+  const double *xn = A.xnode ? A.xnode + (size_t)p * A.N : nullptr;
+  const double h = A.L[p] / (A.N - 1), ih2 = 1.0 / (h * h);
+  double gk[PM_EPT], xk[PM_EPT];
+#pragma unroll
+  for (int q = 0; q < PM_EPT; q++) {
+    const int i = tid + q * PM_T;
+    gk[q] = 0.0; xk[q] = 0.0;
+    if (i < n) {
+      const double psi = sqrt(fmax(ph[i + 1], 1e-12));
+      const double f = A.sign * Fp[i], u = f / psi;
+      const double um = i > 0 ? A.sign * Fp[i - 1] / sqrt(fmax(ph[i], 1e-12)) : 0.0;
+      const double up = i < n - 1 ? A.sign * Fp[i + 1] / sqrt(fmax(ph[i + 2], 1e-12)) : 0.0;
+      double lap;
+      if (!xn) lap = (2.0 * u - um - up) * ih2;
+      else {
+        const double hl = xn[i + 1] - xn[i], hr = xn[i + 2] - xn[i + 1];
+        lap = -2.0 / (hl + hr) * ((up - u) / hr - (u - um) / hl);
+      }
+      gk[q] = -(f + 0.5 * lap / psi);
+      xk[q] = Xk[i];
+      Gk[i] = gk[q];
+    }
+  }
+  __syncthreads();   // G_k visible to the whole CTA
+
+  // ---- Gram matrix of the residual differences and right-hand side (ADM_chen_C.c:89-101), a warp per entry
+  int m = min(A.nm, k - s_kr);
+  if (m > 0) {
+    const int E1 = m * (m + 1) / 2, E = E1 + m;
+    for (int eidx = wid; eidx < E; eidx += PM_NW) {
+      int i, j;
+      if (eidx < E1) { i = 0; int rem = eidx; while (rem >= m - i) { rem -= m - i; i++; } j = i + rem; }
+      else { i = eidx - E1; j = -1; }
+      const double *Gi = Gp + (size_t)((k - i - 1) % R) * n;
+      const double *Gj = j >= 0 ? Gp + (size_t)((k - j - 1) % R) * n : nullptr;
+      double s = 0.0;
+      for (int t = lane; t < n; t += 32) {
+        const double g = Gk[t], di = g - Gi[t];
+        s = fma(di, Gj ? g - Gj[t] : g, s);
+      }
+      s = pm_wsum(s);
+      if (lane == 0) {
+        if (j >= 0) { s_U[i * m + j] = s; s_U[j * m + i] = s; } else s_V[i] = s;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {   // full-pivoting Gauss-Jordan on the m x m system (gaussj.c:19-73), m <= 16
+      int ipiv[PM_NN_MAX];
+      for (int i = 0; i < m; i++) ipiv[i] = 0;
+      bool sing = false;
+      for (int it = 0; it < m && !sing; it++) {
+        double big = -1.0; int irow = -1, icol = -1;
+        for (int j = 0; j < m; j++)
+          if (ipiv[j] != 1)
+            for (int c = 0; c < m; c++)
+              if (ipiv[c] == 0) { const double v = fabs(s_U[j * m + c]); if (v >= big) { big = v; irow = j; icol = c; } }
+        if (irow < 0 || !(big > 0.0) || !isfinite(big)) { sing = true; break; }
+        ipiv[icol]++;
+        if (irow != icol) {
+          for (int l = 0; l < m; l++) { const double tmp = s_U[irow * m + l]; s_U[irow * m + l] = s_U[icol * m + l]; s_U[icol * m + l] = tmp; }
+          const double tmp = s_V[irow]; s_V[irow] = s_V[icol]; s_V[icol] = tmp;
+        }
+        const double pivinv = 1.0 / s_U[icol * m + icol];
+        s_U[icol * m + icol] = 1.0;
+        for (int l = 0; l < m; l++) s_U[icol * m + l] *= pivinv;
+        s_V[icol] *= pivinv;
+        for (int ll = 0; ll < m; ll++)
+          if (ll != icol) {
+            const double dum = s_U[ll * m + icol];
+            s_U[ll * m + icol] = 0.0;
+            for (int l = 0; l < m; l++) s_U[ll * m + l] -= s_U[icol * m + l] * dum;
+            s_V[ll] -= s_V[icol] * dum;
+          }
+      }
+      for (int i = 0; i < m && !sing; i++) if (!isfinite(s_V[i])) sing = true;
+      if (sing) { A.k_restart[p] = k; s_m = 0; } else s_m = m;   // restart with an empty history (ADM_chen_C.c:106-112)
+    }
+    __syncthreads();
+    m = s_m;
+  }
+
+  // ---- X_{k+1} = X_k + sum_j V_j (X_{k-j-1} - X_k) + beta (G_k + sum_j V_j (G_{k-j-1} - G_k))   (ADM_chen_C.c:114-123)
+  double dx[PM_EPT], smax = 0.0;
+#pragma unroll
+  for (int q = 0; q < PM_EPT; q++) {
+    const int i = tid + q * PM_T;
+    dx[q] = 0.0;
+    if (i < n) {
+      double cx = 0.0, cd = 0.0;
+      for (int j = 0; j < m; j++) {
+        const size_t s = (size_t)((k - j - 1) % R) * n + i;
+        cx = fma(s_V[j], Xp[s] - xk[q], cx);
+        cd = fma(s_V[j], Gp[s] - gk[q], cd);
+      }
+      dx[q] = cx + beta * (gk[q] + cd);
+      smax = fmax(smax, fabs(dx[q]));
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, d));
+  if (lane == 0) s_red[wid] = smax;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < PM_NW; w++) s = fmax(s, s_red[w]);
+    s_scalar[0] = (e > 1e-2 && s > A.cap) ? A.cap / s : 1.0;
+  }
+  __syncthreads();
+  const double scale = s_scalar[0];
+#pragma unroll
+  for (int q = 0; q < PM_EPT; q++) {
+    const int i = tid + q * PM_T;
+    if (i < n) Xn[i] = xk[q] + scale * dx[q];
+  }
+}
+
+// ---- batched transfer to the bisected uniform mesh (scft.cc:132-169): not-a-knot spline through the old interior nodes,
+// evaluated at the new interior nodes; one thread per problem, Thomas in transposed scratch (coalesced across problems).
+// Same arithmetic as scftb_refine_mesh (postproc.cu) on x_i = L i/(N-1).
+__global__ void refine_uniform_kernel(int nprob, int N, const double *Lp, const double *eta, long long eta_stride, double *scratch,
+                                      double *eta_new, long long new_stride) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nprob) return;
+  const int Nx = N - 2, m = Nx - 2;
+  const double L = Lp[p];
+  const double *y = eta + (size_t)p * eta_stride;
+  double *out = eta_new + (size_t)p * new_stride;
+  auto xk = [&](int i) { return L * (i + 1) / (N - 1); };   // knot i = old node i+1
+  double *cp = scratch + p, *dp = scratch + (size_t)m * nprob + p, *M = scratch + (size_t)2 * m * nprob + p;   // element i at [i*nprob]
+  const size_t S = nprob;
+  // rows i = 1..m of the second-derivative system with the not-a-knot ends folded in (spline_chen.c:32-56)
+  double a0, b0, aN, bN;
+  { const double h0 = xk(1) - xk(0), h1 = xk(2) - xk(1); a0 = 1.0 + h0 / h1; b0 = -h0 / h1; }
+  { const double g0 = xk(Nx - 1) - xk(Nx - 2), g1 = xk(Nx - 2) - xk(Nx - 3); aN = 1.0 + g0 / g1; bN = -g0 / g1; }
+  double cprev = 0.0, dprev = 0.0;
+  for (int i = 1; i <= m; i++) {
+    const double h0 = xk(i) - xk(i - 1), h1 = xk(i + 1) - xk(i);
+    double lo = h0 / 6., di = (xk(i + 1) - xk(i - 1)) / 3., up = h1 / 6.;
+    const double rh = (y[i + 1] - y[i]) / h1 - (y[i] - y[i - 1]) / h0;
+    if (i == 1) { di += lo * a0; up += lo * b0; }
+    if (i == m) { di += up * aN; lo += up * bN; }
+    if (i == 1) { cprev = up / di; dprev = rh / di; }
+    else { const double den = di - lo * cprev; cprev = up / den; dprev = (rh - lo * dprev) / den; }
+    cp[(size_t)(i - 1) * S] = cprev; dp[(size_t)(i - 1) * S] = dprev;
+  }
+  // back substitution: M[1..m], then the end values
+  double Mn = dp[(size_t)(m - 1) * S];
+  M[(size_t)m * S] = Mn;
+  for (int i = m - 2; i >= 0; i--) { Mn = dp[(size_t)i * S] - cp[(size_t)i * S] * Mn; M[(size_t)(i + 1) * S] = Mn; }
+  M[0] = a0 * M[S] + b0 * M[2 * S];
+  M[(size_t)(Nx - 1) * S] = aN * M[(size_t)(Nx - 2) * S] + bN * M[(size_t)(Nx - 3) * S];
+  // new interior node j = 1..2N-3 sits at old coordinate j/2
+  const int nn = 2 * N - 3;
+  for (int j = 1; j <= nn; j++) {
+    if ((j & 1) == 0) { out[j - 1] = y[j / 2 - 1]; continue; }
+    int klo = (j - 1) / 2 - 1;
+    klo = max(0, min(klo, Nx - 2));
+    const int khi = klo + 1;
+    const double xo = 0.5 * (L * ((j - 1) / 2) / (N - 1) + L * ((j + 1) / 2) / (N - 1));
+    const double hh = xk(khi) - xk(klo), a = (xk(khi) - xo) / hh, b = (xo - xk(klo)) / hh;
+    out[j - 1] = a * y[klo] + b * y[khi] + ((a * a * a - a) * M[(size_t)klo * S] + (b * b * b - b) * M[(size_t)khi * S]) * (hh * hh) / 6.0;
+  }
+}
+
+// weights c[N] with  int eta_h(x) phi_0(x) dx = sum_i c_i eta_i  for the 2^18+1-point Romberg rule of scft.cc:271-281
+// (eta_h piecewise linear on the mesh), and f0bar the way testFiBar.cc:19-50 computes it: the free energy of a field is
+// then (c.eta / f0bar / L + log f0bar) / -1000 (scft.cc:446-447) — the per-(tau, L) work is shared by every problem of a cell
+void free_energy_weights(int N, const double *x /* nullptr = uniform */, double tau, double L, double *c, double *f0bar_out) {
+  std::vector<double> w;
+  const int Mq = (1 << 16) + 1;
+  {
+    std::vector<double> xx(Mq), ff(Mq);
+    for (int i = 0; i < Mq; i++) xx[i] = L / (Mq - 1) * i;
+    f0_given(Mq, xx.data(), tau, ff.data());
+    romberg_weights(Mq - 1, L / (Mq - 1), w);
+    double s = 0;
+    for (int i = 0; i < Mq; i++) s += w[i] * ff[i];
+    *f0bar_out = s / L;
+  }
+  const int nplot = (1 << 18) + 1;
+  std::vector<double> xp(nplot), f0(nplot);
+  for (int i = 0; i < nplot; i++) xp[i] = L * i / (nplot - 1);
+  f0_given(nplot, xp.data(), tau, f0.data());
+  romberg_weights(nplot - 1, L / (nplot - 1), w);
+  std::fill(c, c + N, 0.0);
+  int k = 0;
+  auto xs = [&](int i) { return x ? x[i] : L * i / (N - 1); };
+  for (int i = 0; i < nplot; i++) {
+    while (k < N - 2 && xp[i] > xs(k + 1)) k++;
+    const double t = (xp[i] - xs(k)) / (xs(k + 1) - xs(k)), wf = w[i] * f0[i];
+    c[k] += wf * (1 - t);
+    c[k + 1] += wf * t;
+  }
+}
+
+}  // namespace scftb
+
+using namespace scftb;
+
+struct scftb_pmixer {
+  scftb_engine *e;
+  int nprob, nn, nm, R, k;
+  double tol, cap, blow;
+  double *X, *G, *xbest, *xfinal, *beta, *best, *err;
+  int *k_restart, *done, *iters;
+};
+
+extern "C" {
+
+int scftb_pmixer_destroy(scftb_pmixer *m) {
+  if (!m) return SCFTB_OK;
+  cudaSetDevice(m->e->cfg.device);
+  for (void *p : {(void *)m->X, (void *)m->G, (void *)m->xbest, (void *)m->xfinal, (void *)m->beta, (void *)m->best, (void *)m->err,
+                  (void *)m->k_restart, (void *)m->done, (void *)m->iters})
+    if (p) cudaFree(p);
+  delete m;
+  return SCFTB_OK;
+}
+
+int scftb_pmixer_create(scftb_engine *e, int nprob, double tol, int nn, double cap, scftb_pmixer **out) {
+  if (!e || !out || nprob < 1 || nprob > e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "pmixer: bad argument");
+  if (nn < 0 || nn > PM_NN_MAX) return fail(SCFTB_ERR_ARG, "pmixer: mixing window nn must be in [0, 16]");
+  if (e->ni > PM_T * PM_EPT) return fail(SCFTB_ERR_ARG, "pmixer: more than 4096 unknowns");
+  if (e->diblock_state) return fail(SCFTB_ERR_STATE, "pmixer: one-species engines only");
+  scftb_pmixer *m = new scftb_pmixer();
+  m->e = e; m->nprob = nprob; m->nn = nn; m->nm = std::min(nn, e->ni); m->R = m->nm + 2; m->k = 0;
+  m->tol = tol; m->cap = cap > 0 ? cap : 2.0; m->blow = 10.0;
+  m->X = m->G = m->xbest = m->xfinal = m->beta = m->best = m->err = nullptr;
+  m->k_restart = m->done = m->iters = nullptr;
+  const size_t n = e->ni, ring = (size_t)nprob * m->R * n;
+  CK(cudaSetDevice(e->cfg.device));
+#define CKP(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { int rc = fail(SCFTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); scftb_pmixer_destroy(m); return rc; } } while (0)
+  CKP(cudaMalloc(&m->X, sizeof(double) * ring));
+  CKP(cudaMalloc(&m->G, sizeof(double) * ring));
+  CKP(cudaMalloc(&m->xbest, sizeof(double) * nprob * n));
+  CKP(cudaMalloc(&m->xfinal, sizeof(double) * nprob * n));
+  CKP(cudaMalloc(&m->beta, sizeof(double) * nprob));
+  CKP(cudaMalloc(&m->best, sizeof(double) * nprob));
+  CKP(cudaMalloc(&m->err, sizeof(double) * nprob));
+  CKP(cudaMalloc(&m->k_restart, sizeof(int) * nprob));
+  CKP(cudaMalloc(&m->done, sizeof(int) * nprob));
+  CKP(cudaMalloc(&m->iters, sizeof(int) * nprob));
+  CKP(cudaMemset(m->xfinal, 0, sizeof(double) * nprob * n));
+  CKP(cudaMemset(m->xbest, 0, sizeof(double) * nprob * n));
+  *out = m;
+  return SCFTB_OK;
+}
+
+int scftb_pmixer_reset(scftb_pmixer *m, const double *x, int device, void *stream) {
+  if (!m || !x) return fail(SCFTB_ERR_ARG, "pmixer: null argument");
+  scftb_engine *e = m->e;
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = device ? (cudaStream_t)stream : e->stream;
+  const size_t n = e->ni;
+  CK(cudaMemcpy2DAsync(m->X, sizeof(double) * m->R * n, x, sizeof(double) * n, sizeof(double) * n, m->nprob,
+                       device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  std::vector<double> one(m->nprob, 1.0), inf(m->nprob, INFINITY);
+  CK(cudaMemcpyAsync(m->beta, one.data(), sizeof(double) * m->nprob, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->best, inf.data(), sizeof(double) * m->nprob, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(m->k_restart, 0, sizeof(int) * m->nprob, st));
+  CK(cudaMemsetAsync(m->done, 0, sizeof(int) * m->nprob, st));
+  CK(cudaMemsetAsync(m->iters, 0, sizeof(int) * m->nprob, st));
+  CK(cudaStreamSynchronize(st));   // staging vectors are locals
+  m->k = 0;
+  return SCFTB_OK;
+}
+
+// one iteration of every running problem: F(X_k) and phi by the march, then the preconditioned Anderson update
+int scftb_pmixer_iterate_device(scftb_pmixer *m, void *stream) {
+  if (!m) return fail(SCFTB_ERR_ARG, "pmixer: null argument");
+  scftb_engine *e = m->e;
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (e->params_dirty) {
+    int rc = upload_params(e);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  const long long stride = (long long)m->R * e->ni;
+  const size_t slot = (size_t)(m->k % m->R) * e->ni;
+  int rc = launch_march(e, m->nprob, m->X + slot, stride, e->d_out, e->ni, m->done, st);
+  if (rc) return rc;
+  PMixParams A;
+  A.n = e->ni; A.N = e->cfg.N; A.nprob = m->nprob; A.R = m->R; A.nm = m->nm; A.k = m->k;
+  A.tol = m->tol; A.cap = m->cap; A.blow = m->blow; A.sign = e->cfg.sign;
+  A.F = e->d_out; A.phi = e->d_phi; A.L = e->d_L; A.xnode = e->uniform ? nullptr : e->d_x;
+  A.X = m->X; A.G = m->G; A.xbest = m->xbest; A.xfinal = m->xfinal;
+  A.beta = m->beta; A.best = m->best; A.err = m->err;
+  A.k_restart = m->k_restart; A.done = m->done; A.iters = m->iters;
+  pmix_kernel<<<m->nprob, PM_T, 0, st>>>(A);
+  g_launches++;
+  CK(cudaGetLastError());
+  m->k++;
+  return SCFTB_OK;
+}
+
+int scftb_pmixer_status(scftb_pmixer *m, void *stream, int *done, int *iters, double *err) {
+  if (!m) return fail(SCFTB_ERR_ARG, "pmixer: null argument");
+  CK(cudaSetDevice(m->e->cfg.device));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  if (done) CK(cudaMemcpy(done, m->done, sizeof(int) * m->nprob, cudaMemcpyDeviceToHost));
+  if (iters) CK(cudaMemcpy(iters, m->iters, sizeof(int) * m->nprob, cudaMemcpyDeviceToHost));
+  if (err) CK(cudaMemcpy(err, m->err, sizeof(double) * m->nprob, cudaMemcpyDeviceToHost));
+  return SCFTB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// converged / NaN problems: their final field; running ones: the best iterate so far (the latest one before any evaluation)
+__global__ void pm_gather_kernel(int n, int R, int k, const double *X, const double *xbest, const double *xfinal, const double *best,
+                                 const int *done, double *out) {
+  const int p = blockIdx.x;
+  const double *src = done[p] ? xfinal + (size_t)p * n
+                              : (best[p] < INFINITY ? xbest + (size_t)p * n : X + (size_t)p * R * n + (size_t)(k % R) * n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[(size_t)p * n + i] = src[i];
+}
+}  // namespace
+
+extern "C" {
+
+int scftb_pmixer_get_x(scftb_pmixer *m, void *stream, double *x, int device) {
+  if (!m || !x) return fail(SCFTB_ERR_ARG, "pmixer: null argument");
+  scftb_engine *e = m->e;
+  const size_t n = e->ni;
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  double *dst = x, *tmp = nullptr;
+  if (!device) { CK(cudaMalloc(&tmp, sizeof(double) * m->nprob * n)); dst = tmp; }
+  pm_gather_kernel<<<m->nprob, 256, 0, st>>>((int)n, m->R, m->k, m->X, m->xbest, m->xfinal, m->best, m->done, dst);
+  g_launches++;
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess && !device) ce = cudaMemcpyAsync(x, tmp, sizeof(double) * m->nprob * n, cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess && !device) ce = cudaStreamSynchronize(st);
+  if (tmp) cudaFree(tmp);
+  if (ce != cudaSuccess) return fail(SCFTB_ERR_CUDA, std::string("pmixer_get_x: ") + cudaGetErrorString(ce));
+  return SCFTB_OK;
+}
+
+// run to convergence (all problems) or maxIteration evaluations; the flags are polled from the 5th evaluation on
+static int pmixer_run(scftb_pmixer *m, int maxIteration, std::vector<int> &done, int *evals) {
+  scftb_engine *e = m->e;
+  int rc = SCFTB_OK;
+  bool all = false;
+  done.assign(m->nprob, 0);
+  int k = 0;
+  for (; !rc && k <= maxIteration && !all; k++) {
+    rc = scftb_pmixer_iterate_device(m, e->stream);
+    if (!rc && (k >= 4 || k == maxIteration)) {
+      rc = scftb_pmixer_status(m, e->stream, done.data(), nullptr, nullptr);
+      all = std::all_of(done.begin(), done.end(), [](int d) { return d != 0; });
+    }
+  }
+  if (evals) *evals = k;
+  return rc;
+}
+
+int scftb_padm_batch(scftb_engine *e, int nprob, double *x, double tol, int maxIteration, int nn, int *iters_out, double *err_out) {
+  if (!e || !x || maxIteration < 0) return fail(SCFTB_ERR_ARG, "padm_batch: bad argument");
+  scftb_pmixer *m = nullptr;
+  int rc = scftb_pmixer_create(e, nprob, tol, nn, 0.0, &m);
+  if (rc) return rc;
+  rc = scftb_pmixer_reset(m, x, 0, nullptr);
+  std::vector<int> done, iters(nprob, 0);
+  if (!rc) rc = pmixer_run(m, maxIteration, done, nullptr);
+  if (!rc) rc = scftb_pmixer_status(m, e->stream, done.data(), iters.data(), err_out);
+  if (!rc) rc = scftb_pmixer_get_x(m, e->stream, x, 0);
+  int status = SCFTB_OK;
+  bool nanseen = false;
+  for (int p = 0; p < nprob && !rc; p++) {
+    if (done[p] == 2) nanseen = true;
+    if (done[p] == 0) { status = SCFTB_ERR_NOCONV; iters[p] = m->k; }
+    if (iters_out) iters_out[p] = iters[p];
+  }
+  scftb_pmixer_destroy(m);
+  if (rc) return rc;
+  if (nanseen) return fail(SCFTB_ERR_NAN, "padm_batch: the start field of at least one problem has no finite residual");
+  if (status) fail(status, "padm_batch: iteration limit reached for at least one problem");
+  return status;
+}
+
+int scftb_free_energy_weights(int N, const double *x, double tau, double L, double *c, double *f0bar) {
+  if (N < 4 || !c || !f0bar || !(L > 0)) return fail(SCFTB_ERR_ARG, "free_energy_weights: bad argument");
+  free_energy_weights(N, x, tau, L, c, f0bar);
+  return SCFTB_OK;
+}
+
+int scftb_refine_uniform_batch_device(int nprob, int N, const double *d_L, const double *d_eta, double *d_eta_new, void *stream) {
+  if (nprob < 1 || N < 6 || !d_L || !d_eta || !d_eta_new) return fail(SCFTB_ERR_ARG, "refine_uniform_batch: bad argument");
+  double *scratch = nullptr;
+  const size_t words = (size_t)(3 * (N - 2)) * nprob;
+  CK(cudaMalloc(&scratch, sizeof(double) * words));
+  cudaStream_t st = (cudaStream_t)stream;
+  refine_uniform_kernel<<<(nprob + 63) / 64, 64, 0, st>>>(nprob, N, d_L, d_eta, N - 2, scratch, d_eta_new, 2 * N - 3);
+  g_launches++;
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  cudaFree(scratch);
+  if (ce != cudaSuccess) return fail(SCFTB_ERR_CUDA, std::string("refine_uniform_batch: ") + cudaGetErrorString(ce));
+  return SCFTB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Continuation sweep solver: the reference's driver flow (drivescft.cc:259-322: solve on the coarse mesh, cut every cell,
+// transfer the field by not-a-knot spline, solve again ...) for a whole batch of independent problems in lock-step, with
+// the preconditioned mixer on every level.  Everything between the start fields and the converged fields stays in HBM.
+struct scftb_sweep {
+  scftb_sweep_config cfg;
+  int max_prob;
+  std::vector<int> Ns;
+  std::vector<scftb_engine *> eng;
+  std::vector<scftb_pmixer *> mix;
+  double *d_a = nullptr, *d_b = nullptr;   // ping-pong field buffers [max_prob][N_target-2]
+};
+
+extern "C" {
+
+int scftb_sweep_destroy(scftb_sweep *s) {
+  if (!s) return SCFTB_OK;
+  for (auto *m : s->mix) scftb_pmixer_destroy(m);
+  for (auto *e : s->eng) scftb_destroy(e);
+  if (s->d_a) cudaFree(s->d_a);
+  if (s->d_b) cudaFree(s->d_b);
+  delete s;
+  return SCFTB_OK;
+}
+
+int scftb_sweep_create(const scftb_sweep_config *cfg, int max_prob, scftb_sweep **out) {
+  if (!cfg || !out || max_prob < 1 || cfg->N0 < 6 || cfg->levels < 1) return fail(SCFTB_ERR_ARG, "sweep: bad argument");
+  scftb_sweep *s = new scftb_sweep();
+  s->cfg = *cfg; s->max_prob = max_prob;
+  if (s->cfg.nn <= 0) s->cfg.nn = 10;
+  if (s->cfg.maxit <= 0) s->cfg.maxit = 200;
+  if (!(s->cfg.tol > 0)) s->cfg.tol = 1e-9;
+  int N = cfg->N0;
+  for (int l = 0; l < cfg->levels; l++, N = 2 * N - 1) s->Ns.push_back(N);
+  for (int Nl : s->Ns) {
+    scftb_config ec{};
+    ec.scheme = cfg->scheme; ec.N = Nl; ec.nsteps = cfg->nsteps; ec.quadrature = cfg->quadrature; ec.sign = 1.0;
+    ec.max_batch = max_prob; ec.device = cfg->device; ec.store_history = 0;
+    scftb_engine *e = nullptr;
+    int rc = scftb_create(&ec, &e);
+    if (rc) { scftb_sweep_destroy(s); return rc; }
+    s->eng.push_back(e);
+    scftb_pmixer *m = nullptr;
+    rc = scftb_pmixer_create(e, max_prob, s->cfg.tol, s->cfg.nn, s->cfg.cap, &m);
+    if (rc) { scftb_sweep_destroy(s); return rc; }
+    s->mix.push_back(m);
+  }
+  const size_t words = (size_t)max_prob * (s->Ns.back() - 2);
+  if (cudaMalloc(&s->d_a, sizeof(double) * words) != cudaSuccess || cudaMalloc(&s->d_b, sizeof(double) * words) != cudaSuccess) {
+    scftb_sweep_destroy(s);
+    return fail(SCFTB_ERR_CUDA, "sweep: out of device memory");
+  }
+  *out = s;
+  return SCFTB_OK;
+}
+
+int scftb_sweep_target_N(scftb_sweep *s) { return s ? s->Ns.back() : 0; }
+
+// tau[nprob], L[nprob], eta0[nprob][N0-2] (host) -> eta_out[nprob][N_target-2] (host, may be NULL),
+// rows[nprob][SCFTB_SWEEP_COLS] = {status (0 converged on every level, 1 not, 2 NaN), max|phi0-phi| on the last level reached,
+// evaluations summed over the levels, Q, free energy (scft.cc:446-447 with f0bar of the problem's own (tau, L)),
+// evaluations on the last level, last level reached (N)}; level_seconds[levels] (may be NULL): wall time per level incl. transfer
+int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double *L, const double *eta0, double *eta_out, double *rows,
+                      double *level_seconds) {
+  if (!s || nprob < 1 || nprob > s->max_prob || !tau || !L || !eta0 || !rows) return fail(SCFTB_ERR_ARG, "sweep_solve: bad argument");
+  CK(cudaSetDevice(s->cfg.device));
+  const int levels = (int)s->Ns.size();
+  std::vector<int> done(nprob, 0), iters(nprob, 0), alive(nprob, 1), total(nprob, 0), lastN(nprob, s->Ns[0]), lastIt(nprob, 0), status(nprob, 1);
+  std::vector<double> err(nprob, NAN);
+  // free-energy weights of the target mesh, one set per distinct (tau, L), computed by host threads under the GPU work
+  const int Nt = s->Ns.back();
+  std::map<std::pair<double, double>, int> cell_of;
+  std::vector<std::pair<double, double>> cells;
+  std::vector<int> pcell(nprob);
+  for (int p = 0; p < nprob; p++) {
+    auto key = std::make_pair(tau[p], L[p]);
+    auto it = cell_of.find(key);
+    if (it == cell_of.end()) { it = cell_of.emplace(key, (int)cells.size()).first; cells.push_back(key); }
+    pcell[p] = it->second;
+  }
+  std::vector<double> cw((size_t)cells.size() * Nt), cf0(cells.size());
+  std::vector<std::thread> workers;
+  {
+    const int nthr = (int)std::max(1u, std::min(16u, std::min((unsigned)cells.size(), std::thread::hardware_concurrency())));
+    for (int t = 0; t < nthr; t++)
+      workers.emplace_back([&, t, nthr]() {
+        for (size_t c = t; c < cells.size(); c += nthr)
+          free_energy_weights(Nt, nullptr, cells[c].first, cells[c].second, &cw[c * Nt], &cf0[c]);
+      });
+  }
+  auto join = [&]() { for (auto &w : workers) if (w.joinable()) w.join(); };
+  int rc = SCFTB_OK;
+  double *cur = s->d_a, *nxt = s->d_b;
+  cudaError_t ce = cudaMemcpy(cur, eta0, sizeof(double) * (size_t)nprob * (s->Ns[0] - 2), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { join(); return fail(SCFTB_ERR_CUDA, std::string("sweep_solve: ") + cudaGetErrorString(ce)); }
+  int lvl = 0;
+  for (; lvl < levels && !rc; lvl++) {
+    auto t0 = std::chrono::steady_clock::now();
+    scftb_engine *e = s->eng[lvl];
+    scftb_pmixer *m = s->mix[lvl];
+    for (int p = 0; p < nprob && !rc; p++) rc = scftb_set_problem(e, p, tau[p], L[p], nullptr);
+    if (rc) break;
+    m->nprob = nprob;
+    rc = scftb_pmixer_reset(m, cur, 1, e->stream);
+    if (rc) break;
+    if (lvl) {   // problems that failed on a coarser level stay out
+      std::vector<int> dead(nprob);
+      for (int p = 0; p < nprob; p++) dead[p] = alive[p] ? 0 : 3;
+      ce = cudaMemcpy(m->done, dead.data(), sizeof(int) * nprob, cudaMemcpyHostToDevice);
+      if (ce != cudaSuccess) { rc = fail(SCFTB_ERR_CUDA, cudaGetErrorString(ce)); break; }
+    }
+    rc = pmixer_run(m, s->cfg.maxit, done, nullptr);
+    if (!rc) rc = scftb_pmixer_status(m, e->stream, done.data(), iters.data(), err.data());
+    if (rc) break;
+    for (int p = 0; p < nprob; p++) {
+      if (!alive[p]) continue;
+      const int ev = done[p] ? iters[p] + 1 : m->k;
+      total[p] += ev; lastIt[p] = ev; lastN[p] = s->Ns[lvl];
+      status[p] = done[p] == 1 ? 0 : (done[p] == 2 ? 2 : 1);
+      if (done[p] != 1) alive[p] = 0;
+    }
+    rc = scftb_pmixer_get_x(m, e->stream, cur, 1);
+    if (!rc && lvl + 1 < levels) {
+      rc = scftb_refine_uniform_batch_device(nprob, s->Ns[lvl], e->d_L, cur, nxt, e->stream);
+      std::swap(cur, nxt);
+    } else if (!rc)
+      CK(cudaStreamSynchronize(e->stream));
+    if (level_seconds) level_seconds[lvl] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  join();
+  if (rc) return rc;
+  // results on the target level: fields, Q of the last evaluation, free energy
+  scftb_engine *e = s->eng.back();
+  const int nt = Nt - 2;
+  std::vector<double> eta((size_t)nprob * nt), Q(nprob);
+  CK(cudaMemcpy(eta.data(), cur, sizeof(double) * eta.size(), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(Q.data(), e->d_Q, sizeof(double) * nprob, cudaMemcpyDeviceToHost));
+  if (eta_out) std::copy(eta.begin(), eta.end(), eta_out);
+  for (int p = 0; p < nprob; p++) {
+    double *r = rows + (size_t)p * SCFTB_SWEEP_COLS;
+    r[0] = status[p]; r[1] = err[p]; r[2] = total[p]; r[3] = NAN; r[4] = NAN; r[5] = lastIt[p]; r[6] = lastN[p];
+    if (lastN[p] != Nt) continue;   // stopped on a coarser level: its field is not on the target mesh
+    const double *em = &eta[(size_t)p * nt], *c = &cw[(size_t)pcell[p] * Nt];
+    // wall values of the natural spline on a uniform mesh: linear extrapolation (scft.cc:452-490, march1d.cuh eta_node)
+    double I = c[0] * (2.0 * em[0] - em[1]) + c[Nt - 1] * (2.0 * em[nt - 1] - em[nt - 2]);
+    for (int i = 0; i < nt; i++) I += c[i + 1] * em[i];
+    const double f0bar = cf0[pcell[p]];
+    r[3] = Q[p];
+    r[4] = (I / f0bar / L[p] + std::log(f0bar)) / (-1000.);
+  }
+  return SCFTB_OK;
+}
+
+}  // extern "C"

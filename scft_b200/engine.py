@@ -31,6 +31,14 @@ class _Config(C.Structure):
                 ("sign", C.c_double), ("max_batch", C.c_int), ("device", C.c_int), ("store_history", C.c_int)]
 
 
+class _SweepConfig(C.Structure):
+    _fields_ = [("scheme", C.c_int), ("N0", C.c_int), ("levels", C.c_int), ("nsteps", C.c_int), ("quadrature", C.c_int),
+                ("tol", C.c_double), ("nn", C.c_int), ("maxit", C.c_int), ("cap", C.c_double), ("device", C.c_int)]
+
+
+SWEEP_COLS = 7
+
+
 class _Config2D(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("L", C.c_double), ("Ly", C.c_double), ("tau", C.c_double),
                 ("nsteps", C.c_int), ("quadrature", C.c_int), ("sign", C.c_double), ("rtol", C.c_double),
@@ -45,12 +53,15 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_residual", "scftb_residual_batch", "scftb_residual_batch_device", "scftb_get_phi", "scftb_get_Q",
            "scftb_get_f0_given", "scftb_get_eta_full", "scftb_get_q_history", "scftb_free_energy",
            "scftb_bind_global", "scftb_callback_nr1", "scftb_callback_c0", "scftb_callback_fixedpoint_c0",
-           "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_broydn_device", "scftb_broydn_device_ex", "scftb_adm_chen_batch",
+           "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_broydn_device", "scftb_broydn_device_ex", "scftb_adm_chen_batch", "scftb_adm_batch", "scftb_adm_mixer_create",
            "scftb_set_diblock", "scftb_residual_ab", "scftb_residual_ab_batch", "scftb_get_phi_ab", "scftb_callback_ab_c0",
            "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
            "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_get_y", "scftb_get_slots", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_refine_mesh_adaptive", "scftb_write_solution",
            "scftb_read_solution", "scftb_read_res", "scftb2d_nccl_unique_id", "scftb2d_create", "scftb2d_destroy",
-           "scftb2d_rows", "scftb2d_p2p_handle", "scftb2d_p2p_attach", "scftb2d_p2p_detach", "scftb2d_residual", "scftb2d_get_phi", "scftb2d_get_stats", "scftb2d_export_csr"]
+           "scftb2d_rows", "scftb_pmixer_create", "scftb_pmixer_destroy", "scftb_pmixer_reset", "scftb_pmixer_iterate_device",
+           "scftb_pmixer_status", "scftb_pmixer_get_x", "scftb_padm_batch", "scftb_refine_uniform_batch_device",
+           "scftb_free_energy_weights", "scftb_sweep_create", "scftb_sweep_destroy", "scftb_sweep_target_N", "scftb_sweep_solve",
+           "scftb2d_p2p_handle", "scftb2d_p2p_attach", "scftb2d_p2p_detach", "scftb2d_residual", "scftb2d_get_phi", "scftb2d_get_stats", "scftb2d_export_csr"]
 
 
 def lib():
@@ -89,6 +100,8 @@ def lib():
                                            C.c_int, _ip, _dp]
         L.scftb_mixer_create.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                          C.POINTER(C.c_void_p)]
+        L.scftb_adm_batch.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _ip, _dp]
+        L.scftb_adm_mixer_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.scftb_mixer_destroy.argtypes = [C.c_void_p]
         L.scftb_mixer_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.scftb_mixer_iterate_device.argtypes = [C.c_void_p, C.c_void_p]
@@ -105,6 +118,19 @@ def lib():
         L.scftb_write_solution.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_double, _dp, _dp]
         L.scftb_read_solution.argtypes = [C.c_char_p, _ip, _dp, _dp, C.c_int]
         L.scftb_read_res.argtypes = [C.c_char_p, C.c_int, _dp, _dp, _dp]
+        L.scftb_pmixer_create.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.POINTER(C.c_void_p)]
+        L.scftb_pmixer_destroy.argtypes = [C.c_void_p]
+        L.scftb_pmixer_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.scftb_pmixer_iterate_device.argtypes = [C.c_void_p, C.c_void_p]
+        L.scftb_pmixer_status.argtypes = [C.c_void_p, C.c_void_p, _ip, _ip, _dp]
+        L.scftb_pmixer_get_x.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.scftb_padm_batch.argtypes = [C.c_void_p, C.c_int, _dp, C.c_double, C.c_int, C.c_int, _ip, _dp]
+        L.scftb_refine_uniform_batch_device.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.scftb_free_energy_weights.argtypes = [C.c_int, _dp, C.c_double, C.c_double, _dp, _dp]
+        L.scftb_sweep_create.argtypes = [C.POINTER(_SweepConfig), C.c_int, C.POINTER(C.c_void_p)]
+        L.scftb_sweep_destroy.argtypes = [C.c_void_p]
+        L.scftb_sweep_target_N.argtypes = [C.c_void_p]
+        L.scftb_sweep_solve.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
         L.scftb2d_nccl_unique_id.argtypes = [C.c_char_p]
         L.scftb2d_create.argtypes = [C.POINTER(_Config2D), C.c_char_p, C.POINTER(C.c_void_p)]
         L.scftb2d_destroy.argtypes = [C.c_void_p]
@@ -256,13 +282,31 @@ class Engine:
         return rc, x, iters, err
 
 
-class AndersonBatch:
-    """Device-resident Anderson mixing of a batch (scftb_mixer_*): adm_chen per problem."""
+def _adm_batch(self, x, maxits):
+    """scftb_adm_batch: (rc, x, iteration index per problem, err)"""
+    x = np.ascontiguousarray(x, dtype=np.float64).copy()
+    nprob = 1 if x.ndim == 1 else x.shape[0]
+    iters = np.zeros(nprob, dtype=np.int32)
+    err = np.zeros(nprob)
+    rc = lib().scftb_adm_batch(self._h, nprob, _p(x), maxits, iters.ctypes.data_as(_ip), _p(err))
+    if rc not in (0, 3, 4):
+        _chk(rc)
+    return rc, x, iters, err
 
-    def __init__(self, eng, nprob, tol=1e-7, lmd=0.9, nn=3, final=False):
+
+Engine.adm_batch = _adm_batch
+
+
+class AndersonBatch:
+    """Device-resident Anderson mixing of a batch (scftb_mixer_*): adm_chen per problem (adm=True: adm.c semantics)."""
+
+    def __init__(self, eng, nprob, tol=1e-7, lmd=0.9, nn=3, final=False, adm=False):
         self.eng, self.nprob = eng, nprob
         h = C.c_void_p()
-        _chk(lib().scftb_mixer_create(eng._h, nprob, tol, lmd, nn, int(final), C.byref(h)))
+        if adm:
+            _chk(lib().scftb_adm_mixer_create(eng._h, nprob, C.byref(h)))
+        else:
+            _chk(lib().scftb_mixer_create(eng._h, nprob, tol, lmd, nn, int(final), C.byref(h)))
         self._h = h
 
     def close(self):
@@ -303,6 +347,93 @@ class AndersonBatch:
         out = np.zeros((self.nprob, self.eng.ni))
         _chk(lib().scftb_mixer_get_y(self._h, C.c_void_p(stream_ptr), k, _p(out)))
         return out
+
+
+class PrecondAndersonBatch:
+    """Device-resident preconditioned Anderson mixing of a batch (scftb_pmixer_*)."""
+
+    def __init__(self, eng, nprob, tol=1e-9, nn=10, cap=2.0):
+        self.eng, self.nprob = eng, nprob
+        h = C.c_void_p()
+        _chk(lib().scftb_pmixer_create(eng._h, nprob, tol, nn, cap, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().scftb_pmixer_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        _chk(lib().scftb_pmixer_reset(self._h, C.c_void_p(x.ctypes.data), 0, None))
+
+    def iterate_device(self, stream_ptr=0):
+        _chk(lib().scftb_pmixer_iterate_device(self._h, C.c_void_p(stream_ptr)))
+
+    def status(self, stream_ptr=0):
+        done = np.zeros(self.nprob, dtype=np.int32)
+        iters = np.zeros(self.nprob, dtype=np.int32)
+        err = np.zeros(self.nprob)
+        _chk(lib().scftb_pmixer_status(self._h, C.c_void_p(stream_ptr), done.ctypes.data_as(_ip),
+                                       iters.ctypes.data_as(_ip), _p(err)))
+        return done, iters, err
+
+    def x(self, stream_ptr=0):
+        out = np.zeros((self.nprob, self.eng.ni))
+        _chk(lib().scftb_pmixer_get_x(self._h, C.c_void_p(stream_ptr), C.c_void_p(out.ctypes.data), 0))
+        return out
+
+
+def padm_batch(eng, x, tol=1e-9, max_iteration=200, nn=10):
+    """scftb_padm_batch: (rc, x, evaluations-1 per problem, err)"""
+    x = np.ascontiguousarray(x, dtype=np.float64).copy()
+    nprob = 1 if x.ndim == 1 else x.shape[0]
+    iters = np.zeros(nprob, dtype=np.int32)
+    err = np.zeros(nprob)
+    rc = lib().scftb_padm_batch(eng._h, nprob, _p(x), tol, max_iteration, nn, iters.ctypes.data_as(_ip), _p(err))
+    if rc not in (0, 3, 4):
+        _chk(rc)
+    return rc, x, iters, err
+
+
+def free_energy_weights(N, tau, L, x=None):
+    """scftb_free_energy_weights: (c[N], f0bar)"""
+    c, f0bar = np.zeros(N), C.c_double(0)
+    xa = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+    _chk(lib().scftb_free_energy_weights(N, _p(xa) if xa is not None else None, tau, L, _p(c), C.byref(f0bar)))
+    return c, f0bar.value
+
+
+class SweepSolver:
+    """scftb_sweep_*: continuation N0 -> ... -> N_target with preconditioned mixing for a batch of problems."""
+
+    def __init__(self, max_prob, N0=33, levels=6, nsteps=2048, scheme=IE_ROWSCALE, quadrature=QUAD_ROMBERG, tol=1e-9, nn=10,
+                 maxit=200, cap=2.0, device=0):
+        cfg = _SweepConfig(scheme, N0, levels, nsteps, quadrature, tol, nn, maxit, cap, device)
+        h = C.c_void_p()
+        _chk(lib().scftb_sweep_create(C.byref(cfg), max_prob, C.byref(h)))
+        self._h, self.N0, self.levels, self.max_prob = h, N0, levels, max_prob
+        self.N_target = lib().scftb_sweep_target_N(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().scftb_sweep_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def solve(self, taus, Ls, eta0, want_fields=True):
+        """-> dict(rows [nprob, 7] (status, err, evals, Q, F, evals_last_level, N_last), eta [nprob, N_target-2], level_seconds)"""
+        taus, Ls, eta0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (taus, Ls, eta0))
+        nprob = len(taus)
+        assert eta0.shape == (nprob, self.N0 - 2)
+        rows = np.zeros((nprob, SWEEP_COLS))
+        eta = np.zeros((nprob, self.N_target - 2)) if want_fields else None
+        secs = np.zeros(self.levels)
+        _chk(lib().scftb_sweep_solve(self._h, nprob, _p(taus), _p(Ls), _p(eta0), _p(eta) if want_fields else None, _p(rows), _p(secs)))
+        return dict(rows=rows, eta=eta, level_seconds=secs)
 
 
 def spline(x, y, xp, mode=0, bc=0.0):

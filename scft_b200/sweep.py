@@ -162,3 +162,28 @@ def converge_block(p0, p1, eta33_mid, N_target=1025, nsteps=2048, scheme=None, d
 
 
 converge_block.last_wall = 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# The same continuation for a whole block of the sweep in lock-step on the device (scftb_sweep_*): preconditioned
+# Anderson mixing on every level, fields, history rings and the mesh transfer resident in HBM.
+def converge_block_batched(p0, p1, eta33_mid, levels=6, nsteps=2048, scheme=None, device=0, tol=1e-9, nn=10, solver=None,
+                           want_fields=False):
+    """Converge sweep problems [p0, p1).  Returns dict(rows [p1-p0, 7] = (status, err, evaluations, Q, F,
+    evaluations on the target mesh, N reached), seconds (solve phase), level_seconds, eta (if want_fields))."""
+    import time
+    from . import engine as E
+    count = p1 - p0
+    taus, Ls, eta0 = make_sweep(p0, count, np.asarray(eta33_mid, dtype=np.float64))
+    own = solver is None
+    if own:
+        solver = E.SweepSolver(count, N0=len(eta33_mid) + 2, levels=levels, nsteps=nsteps,
+                               scheme=E.IE_ROWSCALE if scheme is None else scheme, tol=tol, nn=nn, device=device)
+    try:
+        t0 = time.perf_counter()
+        r = solver.solve(taus, Ls, eta0, want_fields=want_fields)
+        r["seconds"] = time.perf_counter() - t0
+    finally:
+        if own:
+            solver.close()
+    return r

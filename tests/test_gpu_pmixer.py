@@ -1,0 +1,130 @@
+"""Preconditioned Anderson mixing (scftb_pmixer_*, scftb_padm_batch) and the batched continuation (scftb_sweep_*):
+converged fields are checked by the CPU oracle (residual, Q, free energy) and against the reference-shaped Broyden flow."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_check(N, tau, L, eta_mid, scheme=O.IE_ROWSCALE, nsteps=2048):
+    x = O.mesh_uniform(N, L)
+    ef = O.eta_full(x, eta_mid)
+    ref = O.residual(ef, O.f0_given(x, tau), scheme=scheme, nsteps=nsteps, L=L)
+    F = O.free_energy(x, ef, tau=tau, L=L, f0bar_=O.f0bar(tau, L))
+    return np.max(np.abs(ref["out"])), ref["Q"], F
+
+
+def test_padm_batch_converges_in_few_evaluations(fixtures):
+    """N=129: 16 sweep problems from the interpolated reference field converge in <= 40 evaluations each (the reference's
+    staged adm_chen needs thousands, profiles/r1_continuation_m1024.txt) and the oracle confirms every field"""
+    import scft_b200 as S
+    from scft_b200 import sweep
+    eta33 = fixtures["n33_eta"][1:-1]
+    N, nprob = 129, 16
+    eng = S.Engine(N, nsteps=2048, scheme=S.IE_ROWSCALE, max_batch=nprob)
+    x0 = np.zeros((nprob, N - 2))
+    pars = []
+    for i in range(nprob):
+        tau, L, _ = sweep.sweep_params(i * 17)
+        pars.append((tau, L))
+        eng.set_problem(i, tau, L)
+        xs, e = np.linspace(0, L, 33), eta33
+        for _ in range(2):
+            xs, e = S.refine_mesh(xs, e)
+        x0[i] = e
+    rc, x, iters, err = S.padm_batch(eng, x0, tol=1e-9, max_iteration=100, nn=10)
+    assert rc == 0 and np.all(err < 1e-9) and iters.max() <= 40, (rc, iters, err)
+    for i in (0, 5, 15):
+        tau, L = pars[i]
+        r, Q, _ = _oracle_check(N, tau, L, x[i])
+        assert r < 2e-9
+        assert abs(Q - eng.Q(i)) <= 1e-10 * abs(Q)
+    eng.close()
+
+
+def test_padm_matches_broyden_fixed_point(fixtures):
+    """same discrete problem, two solvers: the preconditioned mixer and the reference-shaped device Broyden agree on the
+    converged state (phi, Q to 1e-9; free energy to 1e-9 relative)"""
+    import scft_b200 as S
+    eta33 = fixtures["n33_eta"][1:-1]
+    N = 65
+    xs, e = S.refine_mesh(np.linspace(0, S.L_REF, 33), eta33)
+    eng = S.Engine(N, nsteps=2048, scheme=S.IE_ROWSCALE, max_batch=N - 2)
+    rc, xa, _, erra = S.padm_batch(eng, e[None, :], tol=1e-12, max_iteration=100)
+    assert rc == 0 and erra[0] < 1e-12
+    eng.residual(xa[0])
+    phia, Qa, Fa = eng.phi(0), eng.Q(0), eng.free_energy(0)
+    _, check, xb, errb, _ = eng.broydn_device(e, 1e-10, keep_trial=True)
+    assert check == 0 and errb < 1e-10
+    eng.residual(xb)
+    phib, Qb, Fb = eng.phi(0), eng.Q(0), eng.free_energy(0)
+    got = (np.max(np.abs(phia - phib)), abs(Qa - Qb) / Qb, abs(Fa - Fb) / abs(Fb), np.max(np.abs(xa[0] - xb)[8:-8]))
+    # the field itself is determined up to tol x |J^-1| (6e3 at the wall nodes of this mesh): compare where J is O(1)
+    assert got[0] < 1e-9 and got[1] < 1e-9 and got[2] < 1e-9 and got[3] < 1e-6, got
+    eng.close()
+
+
+@pytest.mark.parametrize("scheme_name", ["IE_ROWSCALE", "IE_CONSISTENT", "IRK4_CONSISTENT"])
+def test_padm_all_schemes(fixtures, scheme_name):
+    import scft_b200 as S
+    scheme = getattr(S, scheme_name)
+    eta33 = fixtures["n33_eta"][1:-1]
+    eng = S.Engine(33, nsteps=2048, scheme=scheme, max_batch=4)
+    x0 = np.stack([eta33 * (1 + 0.05 * np.random.default_rng(s).standard_normal(31)) for s in range(4)])
+    rc, x, iters, err = S.padm_batch(eng, x0, tol=1e-9, max_iteration=200)
+    assert rc == 0 and np.all(err < 1e-9), (rc, iters, err)
+    r, _, _ = _oracle_check(33, S.TAU_REF, S.L_REF, x[2], scheme=getattr(O, scheme_name))
+    assert r < 2e-9
+    eng.close()
+
+
+def test_refine_batch_equals_host_refine(fixtures):
+    import torch
+    import scft_b200 as S
+    import ctypes as C
+    eta33 = fixtures["n33_eta"][1:-1]
+    Ls = np.array([3.2, 3.72374357332160, 4.2])
+    eta = np.stack([eta33 * (1 + 0.1 * k) for k in range(3)])
+    d_L = torch.from_numpy(Ls).cuda()
+    d_eta = torch.from_numpy(eta).cuda()
+    d_new = torch.zeros((3, 63), dtype=torch.float64, device="cuda")
+    rc = S.lib().scftb_refine_uniform_batch_device(3, 33, C.c_void_p(d_L.data_ptr()), C.c_void_p(d_eta.data_ptr()),
+                                                   C.c_void_p(d_new.data_ptr()), None)
+    assert rc == 0
+    got = d_new.cpu().numpy()
+    for k in range(3):
+        _, ref = S.refine_mesh(np.linspace(0, Ls[k], 33), eta[k])
+        assert np.max(np.abs(got[k] - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def test_free_energy_weights_equal_free_energy(fixtures):
+    import scft_b200 as S
+    eta33 = fixtures["n33_eta"][1:-1]
+    eng = S.Engine(33, nsteps=2048, scheme=S.IRK4_CONSISTENT)
+    eng.residual(eta33)
+    F = eng.free_energy(0, f0bar=0.0)
+    c, f0bar = S.free_energy_weights(33, S.TAU_REF, S.L_REF)
+    F2 = (c @ eng.eta_full(0) / f0bar / S.L_REF + np.log(f0bar)) / -1000.0
+    assert abs(F - F2) <= 1e-13 * abs(F)
+    eng.close()
+
+
+def test_sweep_solver_continuation_to_257(fixtures):
+    """batched continuation 33 -> 65 -> 129 -> 257 of 64 sweep problems: all converge; oracle-checked residual, Q, F; the
+    16 seeds of one (tau, L) cell end in the same state"""
+    from scft_b200 import sweep
+    eta33 = fixtures["n33_eta"][1:-1]
+    r = sweep.converge_block_batched(0, 64, eta33, levels=4, want_fields=True)
+    rows = r["rows"]
+    assert np.all(rows[:, 0] == 0) and np.all(rows[:, 1] < 1e-9) and np.all(rows[:, 6] == 257), rows[rows[:, 0] != 0]
+    assert rows[:, 5].max() <= 20            # evaluations on the target mesh
+    for p in (0, 17, 63):
+        tau, L, _ = sweep.sweep_params(p)
+        res, Q, F = _oracle_check(257, tau, L, r["eta"][p])
+        assert res < 2e-9
+        assert abs(Q - rows[p, 3]) <= 1e-10 * abs(Q)
+        assert abs(F - rows[p, 4]) <= 1e-9 * abs(F)
+    r2 = sweep.converge_block_batched(256, 258, eta33, levels=4)     # same cells as problems 0, 1; other seeds
+    assert np.max(np.abs(r2["rows"][:, 4] - rows[:2, 4])) <= 1e-9 * np.abs(rows[:2, 4]).max()
