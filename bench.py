@@ -6,7 +6,8 @@ SCFT problems over (tau, L, perturbed eta0), m=1024 elements (N=1025 nodes, 1023
 n=2048 implicit-Euler contour steps, P=1 propagator sweep per evaluation (the reference's
 symmetric one-sweep form q+(x,s)=q(x,1-s), drivescft.cc:189-190).  One "step" is one SCFT
 iteration of every problem of the batch: a residual evaluation (the march kernel) followed by
-the field update.  The 4096 problems of the sweep are sharded across the ranks in contiguous blocks with no
+the field update (preconditioned Anderson mixing, scft_b200/csrc/pmixer.cu) on the target mesh, started from the
+fields the continuation hands to that mesh (coarser levels solved, field transferred by spline).  The 4096 problems of the sweep are sharded across the ranks in contiguous blocks with no
 data-path collective: STRONG scaling (4096 / N problems per GPU), as BASELINE.json words configs[2].  At N > 1 a
 second, weak-scaling leg (4096 problems per GPU) is reported under the extra key "weak".
 
@@ -36,10 +37,20 @@ BYTES_PER_DOF_STEP = 8.0  # lean history: each q(x_i,s_j), j<n/2, is written onc
 
 
 def make_sweep(first, count):
-    """problems [first, first+count) of the sweep (scft_b200/sweep.py)"""
+    """problems [first, first+count) of the sweep (scft_b200/sweep.py) with fields on the target
+    mesh: the perturbed spectral guess (used by the CPU legs, which only evaluate residuals)"""
     from scft_b200 import sweep
     fx = np.load(os.path.join(ROOT, "tests", "golden", "ref_fixtures.npz"))
     return sweep.make_sweep(first, count, fx["res1024_eta"][1:-1])
+
+
+def eta33_start():
+    """the reference's own start field (DEALII_SCFT/inputFiles/N=33_for_read.txt, drivescft.cc:264), interior nodes"""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "ref_fixtures.npz"))
+    return fx["n33_eta"][1:-1]
+
+
+LEVELS = 6   # 33 -> 65 -> 129 -> 257 -> 513 -> 1025 (drivescft.cc:291-322: refine every cell, solve again)
 
 
 class ClockSampler:
@@ -204,25 +215,36 @@ def workload_config(problems_per_gpu, world, total=TOTAL_PROBLEMS):
 
 
 class SweepRun:
-    """problems [p0, p1) of the sweep resident on this rank's GPU: engine + device-resident Anderson mixer"""
+    """problems [p0, p1) of the sweep resident on this rank's GPU: engine + device-resident preconditioned mixer.
+    The start fields of the timed iterations are what the continuation hands to the target mesh: levels 33..513 solved
+    (untimed preparation here; the whole flow is timed by the sweep_converged leg), field cut to 1025 nodes by spline."""
 
     def __init__(self, p0, p1, local, torch, scft_b200):
+        import ctypes as C
+        from scft_b200 import sweep
         self.P = p1 - p0
-        self.taus, self.Ls, self.eta = make_sweep(p0, self.P)
+        dev = torch.device("cuda", local)
+        self.taus, self.Ls, eta0 = sweep.make_sweep(p0, self.P, eta33_start())
+        coarse = scft_b200.SweepSolver(self.P, N0=33, levels=LEVELS - 1, nsteps=NSTEPS, scheme=SCHEME, device=local)
+        r = coarse.solve(self.taus, self.Ls, eta0)
+        coarse.close()
+        self.coarse_converged = int((r["rows"][:, 0] == 0).sum())
+        d_c = torch.from_numpy(r["eta"]).to(dev)
+        d_L = torch.from_numpy(self.Ls).to(dev)
+        self.d_eta = torch.zeros((self.P, N_NODES - 2), dtype=torch.float64, device=dev)
+        rc = scft_b200.lib().scftb_refine_uniform_batch_device(self.P, (N_NODES + 1) // 2, C.c_void_p(d_L.data_ptr()),
+                                                               C.c_void_p(d_c.data_ptr()), C.c_void_p(self.d_eta.data_ptr()), None)
+        assert rc == 0
         self.eng = scft_b200.Engine(N_NODES, nsteps=NSTEPS, scheme=SCHEME, max_batch=self.P, device=local)
         for p in range(self.P):
             self.eng.set_problem(p, self.taus[p], self.Ls[p])
-        dev = torch.device("cuda", local)
-        self.h_eta = torch.from_numpy(self.eta).pin_memory()
+        self.h_eta = self.d_eta.cpu().pin_memory()
+        self.eta = self.h_eta.numpy()
         self.h_out = torch.empty_like(self.h_eta).pin_memory()
-        self.d_eta = self.h_eta.to(dev, non_blocking=True)
         self.stream = torch.cuda.current_stream()
-        # relaxation of the reference's first Anderson stage (adm_chen(..., 0.99, 2), drivescft.cc:294) with a window of
-        # ONE: from the perturbed spectral guess the two-vector extrapolation overshoots on ~1 % of the 4096 problems
-        # (residuals overflow after ~10 iterations, tools/mixer_stability.py), the one-vector window keeps every problem
-        # finite and descending.  tol unreachable and freeze off, so EVERY problem is evaluated in EVERY step.
-        self.mixer = scft_b200.AndersonBatch(self.eng, self.P, tol=1e-30, lmd=0.99, nn=1)
-        self.mixer.set_freeze(False)
+        # tol = 0: no problem is ever frozen, so EVERY problem is evaluated and updated in EVERY step; the iterates reach
+        # max|phi0 - phi| < 1e-9 after ~8 steps and stay at round-off level afterwards
+        self.mixer = scft_b200.PrecondAndersonBatch(self.eng, self.P, tol=0.0, nn=10)
         self.mixer.reset_device(self.d_eta.data_ptr(), self.stream.cuda_stream)
 
     def step(self):
@@ -339,7 +361,7 @@ def main():
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     ms_total, march_ms_avg = max_over_ranks([ms, march_ms])
     done, iters, err = run.mixer.status(run.stream.cuda_stream)
-    finite_local = float(np.isfinite(err).sum())
+    kernel_name = run.eng.kernel_name()
 
     # ---- end to end through the C ABI with host buffers (H2D + kernel + D2H inside the call)
     barrier()
@@ -361,6 +383,18 @@ def main():
     allres = sweep.gather_results(local_rows, total, rank, world) if world > 1 else local_rows
     run.close()
 
+    # ---- the sweep to convergence, for real: every problem of this rank's block from the N=33 start field through all
+    # levels to max|phi0 - phi| < 1e-9 on the target mesh; wall clock from host start fields to host result rows
+    solver = scft_b200.SweepSolver(P, N0=33, levels=LEVELS, nsteps=NSTEPS, scheme=SCHEME, tol=1e-9, device=local)
+    conv = sweep.converge_block_batched(p0, p1, eta33_start(), levels=LEVELS, solver=solver)          # warm-up pass
+    barrier()
+    t0 = time.perf_counter()
+    conv = sweep.converge_block_batched(p0, p1, eta33_start(), levels=LEVELS, solver=solver)
+    torch.cuda.synchronize()
+    conv_s = max_over_ranks([time.perf_counter() - t0])[0]
+    solver.close()
+    conv_rows = sweep.gather_results(conv["rows"], total, rank, world) if world > 1 else conv["rows"]
+
     # ---- extra: weak scaling (4096 problems on every GPU), N > 1 only
     weak = None
     if world > 1 and not args.no_weak:
@@ -368,7 +402,7 @@ def main():
         wms, wmarch, _ = timed_steps(wrun, args.steps, args.warmup, barrier, torch)
         wms, wmarch = max_over_ranks([wms, wmarch])
         wrun.close()
-        weak = {"scaling": "weak", "problems_per_gpu": TOTAL_PROBLEMS,
+        weak = {"scaling": "weak", "problems_per_gpu": TOTAL_PROBLEMS, "problems_total": world * TOTAL_PROBLEMS,
                 "value": world * TOTAL_PROBLEMS * ni * NSTEPS * args.steps / (wms * 1e-3), "unit": "DOF-steps/s",
                 "ms_per_step": wms / args.steps, "march_kernel_ms": wmarch,
                 "hbm_frac_per_gpu": TOTAL_PROBLEMS * ni * NSTEPS * BYTES_PER_DOF_STEP / (wmarch * 1e-3) / 1e9}
@@ -391,7 +425,7 @@ def main():
         for name in ("r2_traffic.json", "r1_traffic.json"):
             tpath = os.path.join(ROOT, "profiles", name)
             if os.path.exists(tpath):
-                tr = json.load(open(tpath))["march_ie_kernel"]
+                tr = json.load(open(tpath))["march_kernel"]
                 if tr["N"] == N_NODES and tr["nsteps"] == NSTEPS:   # per-launch traffic scales with the problem count
                     traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * Pmax / tr["problems"]
                     break
@@ -402,6 +436,23 @@ def main():
                 "config": workload_config(Pmax, world, total),
                 "scft_iterations_per_s": total * args.steps / (ms_total * 1e-3),
                 "problems_with_finite_residual_at_end": finite,
+                "problems_below_1e-9_at_end": int((allres[:, 0] < 1e-9).sum()),
+                "worst_residual_at_end": float(np.nanmax(allres[:, 0])),
+                "field_update": "preconditioned Anderson mixing (pmix_kernel), window 10, never frozen (tol 0)",
+                "sweep_converged": {
+                    "problems": total, "converged": int((conv_rows[:, 0] == 0).sum()), "tol": 1e-9,
+                    "seconds": conv_s, "problems_per_s": total / conv_s,
+                    "worst_residual": float(np.nanmax(conv_rows[:, 1])),
+                    "evaluations_per_problem_mean": float(conv_rows[:, 2].mean()),
+                    "evaluations_per_problem_max": float(conv_rows[:, 2].max()),
+                    "target_mesh_evaluations_mean": float(conv_rows[:, 5].mean()),
+                    "target_mesh_evaluations_max": float(conv_rows[:, 5].max()),
+                    "free_energy_range": [float(np.nanmin(conv_rows[:, 4])), float(np.nanmax(conv_rows[:, 4]))],
+                    "rank0_seconds_per_level_then_host_wait": [round(float(v), 4) for v in conv["level_seconds"]],
+                    "rank0_seconds_start_fields": round(float(conv.get("seconds_make_sweep", 0.0)), 4),
+                    "flow": "continuation N=33->65->129->257->513->1025 (drivescft.cc:291-322), preconditioned Anderson mixing on "
+                            "every level, all problems of a rank in lock-step on the device; wall clock from host start fields "
+                            "to host result rows, max over ranks; no extrapolation"},
                 "parity_checked": checked * world, "max_rel_err": max_rel_all,
                 "parity": "phi, Q, residual of sampled problems vs the CPU oracle (oracle/scft_oracle.c), tolerance 1e-10",
                 "clocks": clocks,
@@ -410,7 +461,7 @@ def main():
                         "call": "scftb_residual_batch (pinned host buffers), wall clock, max over ranks; bytes per rank"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "march_ie_kernel<8,128,uniform>",
+                             "traffic": traffic, "kernel": kernel_name,
                              "problems_per_launch": Pmax,
                              "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": march_ms_avg,
                              "peak_source": peak_src,

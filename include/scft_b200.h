@@ -230,7 +230,8 @@ int scftb_sweep_target_N(scftb_sweep *s);
 /* tau[nprob], L[nprob], eta0[nprob][N0-2] (host) -> eta_out[nprob][N_target-2] (host, may be NULL) and
  * rows[nprob][SCFTB_SWEEP_COLS] = { status (0 converged on every level / 1 not / 2 NaN), max|phi0-phi| on the last level
  * reached, evaluations summed over the levels, Q, free energy (f0bar of the problem's own (tau, L)), evaluations on the
- * last level, N of the last level reached }; level_seconds[levels] (may be NULL) */
+ * last level, N of the last level reached }; level_seconds[levels + 1] (may be NULL): wall seconds per level, then the
+ * wait for the host threads that prepare the free-energy weights */
 int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double *L, const double *eta0, double *eta_out,
                       double *rows, double *level_seconds);
 
@@ -298,6 +299,8 @@ int scftb_set_timing(scftb_engine *e, int on);
 int scftb_get_march_ms(scftb_engine *e, double *total_ms, int *count);
 /* resident CTA slots of the march kernel on this device (= problems per wave; lean history is kept per slot) */
 int scftb_get_slots(scftb_engine *e, int *slots);
+/* name and CTA shape of the march kernel this engine launches (bench evidence) */
+int scftb_get_kernel_name(scftb_engine *e, char *buf, int len);
 
 #ifdef __cplusplus
 }

@@ -333,6 +333,14 @@ int scftb_get_march_ms(scftb_engine *e, double *total_ms, int *count) {
 
 int scftb_engine_max_batch(scftb_engine *e) { return e ? e->cfg.max_batch : 0; }
 
+int scftb_get_kernel_name(scftb_engine *e, char *buf, int len) {
+  if (!e || !buf || len < 1) return fail(SCFTB_ERR_ARG, "null argument");
+  const bool tm = e->kc.fn == (march_fn)march_tm_kernel;
+  snprintf(buf, len, "%s<%d,%d,%s>%s", e->cfg.scheme == SCFTB_IRK4_CONSISTENT ? "march_irk4_kernel" : (tm ? "march_tm_kernel" : "march_ie_kernel"),
+           e->kc.C, e->kc.T, e->uniform ? "uniform" : "mesh", tm ? " (coefficients in tensor memory)" : "");
+  return SCFTB_OK;
+}
+
 int scftb_get_slots(scftb_engine *e, int *slots) {
   if (!e || !slots) return fail(SCFTB_ERR_ARG, "null argument");
   *slots = e->slots;

@@ -573,7 +573,8 @@ int scftb_sweep_target_N(scftb_sweep *s) { return s ? s->Ns.back() : 0; }
 // tau[nprob], L[nprob], eta0[nprob][N0-2] (host) -> eta_out[nprob][N_target-2] (host, may be NULL),
 // rows[nprob][SCFTB_SWEEP_COLS] = {status (0 converged on every level, 1 not, 2 NaN), max|phi0-phi| on the last level reached,
 // evaluations summed over the levels, Q, free energy (scft.cc:446-447 with f0bar of the problem's own (tau, L)),
-// evaluations on the last level, last level reached (N)}; level_seconds[levels] (may be NULL): wall time per level incl. transfer
+// evaluations on the last level, last level reached (N)}; level_seconds[levels + 1] (may be NULL): wall time per level incl.
+// transfer, then the time spent waiting for the host threads that prepare the free-energy weights
 int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double *L, const double *eta0, double *eta_out, double *rows,
                       double *level_seconds) {
   if (!s || nprob < 1 || nprob > s->max_prob || !tau || !L || !eta0 || !rows) return fail(SCFTB_ERR_ARG, "sweep_solve: bad argument");
@@ -641,7 +642,9 @@ int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double
       CK(cudaStreamSynchronize(e->stream));
     if (level_seconds) level_seconds[lvl] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
+  auto tj = std::chrono::steady_clock::now();
   join();
+  if (level_seconds) level_seconds[levels] = std::chrono::duration<double>(std::chrono::steady_clock::now() - tj).count();
   if (rc) return rc;
   // results on the target level: fields, Q of the last evaluation, free energy
   scftb_engine *e = s->eng.back();

@@ -56,7 +56,7 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_funcerr", "scftb_adm_chen", "scftb_adm", "scftb_broydn", "scftb_broydn_device", "scftb_broydn_device_ex", "scftb_adm_chen_batch", "scftb_adm_batch", "scftb_adm_mixer_create",
            "scftb_set_diblock", "scftb_residual_ab", "scftb_residual_ab_batch", "scftb_get_phi_ab", "scftb_callback_ab_c0",
            "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
-           "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_get_y", "scftb_get_slots", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_refine_mesh_adaptive", "scftb_write_solution",
+           "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_get_y", "scftb_get_slots", "scftb_get_kernel_name", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_refine_mesh_adaptive", "scftb_write_solution",
            "scftb_read_solution", "scftb_read_res", "scftb2d_nccl_unique_id", "scftb2d_create", "scftb2d_destroy",
            "scftb2d_rows", "scftb_pmixer_create", "scftb_pmixer_destroy", "scftb_pmixer_reset", "scftb_pmixer_iterate_device",
            "scftb_pmixer_status", "scftb_pmixer_get_x", "scftb_padm_batch", "scftb_refine_uniform_batch_device",
@@ -110,6 +110,7 @@ def lib():
         L.scftb_mixer_get_x.argtypes = [C.c_void_p, C.c_void_p, _dp]
         L.scftb_mixer_get_y.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp]
         L.scftb_get_slots.argtypes = [C.c_void_p, _ip]
+        L.scftb_get_kernel_name.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.scftb_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.scftb_get_march_ms.argtypes = [C.c_void_p, _dp, _ip]
         L.scftb_spline.argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double]
@@ -209,6 +210,11 @@ class Engine:
         v = C.c_int(0)
         _chk(lib().scftb_get_slots(self._h, C.byref(v)))
         return v.value
+
+    def kernel_name(self):
+        buf = C.create_string_buffer(128)
+        _chk(lib().scftb_get_kernel_name(self._h, buf, 128))
+        return buf.value.decode()
 
     def residual_device(self, nprob, d_eta_ptr, d_out_ptr, stream_ptr=0):
         _chk(lib().scftb_residual_batch_device(self._h, nprob, C.c_void_p(d_eta_ptr), C.c_void_p(d_out_ptr),
@@ -369,6 +375,9 @@ class PrecondAndersonBatch:
         x = np.ascontiguousarray(x, dtype=np.float64)
         _chk(lib().scftb_pmixer_reset(self._h, C.c_void_p(x.ctypes.data), 0, None))
 
+    def reset_device(self, d_x_ptr, stream_ptr=0):
+        _chk(lib().scftb_pmixer_reset(self._h, C.c_void_p(d_x_ptr), 1, C.c_void_p(stream_ptr)))
+
     def iterate_device(self, stream_ptr=0):
         _chk(lib().scftb_pmixer_iterate_device(self._h, C.c_void_p(stream_ptr)))
 
@@ -431,7 +440,7 @@ class SweepSolver:
         assert eta0.shape == (nprob, self.N0 - 2)
         rows = np.zeros((nprob, SWEEP_COLS))
         eta = np.zeros((nprob, self.N_target - 2)) if want_fields else None
-        secs = np.zeros(self.levels)
+        secs = np.zeros(self.levels + 1)
         _chk(lib().scftb_sweep_solve(self._h, nprob, _p(taus), _p(Ls), _p(eta0), _p(eta) if want_fields else None, _p(rows), _p(secs)))
         return dict(rows=rows, eta=eta, level_seconds=secs)
 

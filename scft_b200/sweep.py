@@ -174,7 +174,9 @@ def converge_block_batched(p0, p1, eta33_mid, levels=6, nsteps=2048, scheme=None
     import time
     from . import engine as E
     count = p1 - p0
+    t_ms = time.perf_counter()
     taus, Ls, eta0 = make_sweep(p0, count, np.asarray(eta33_mid, dtype=np.float64))
+    t_ms = time.perf_counter() - t_ms
     own = solver is None
     if own:
         solver = E.SweepSolver(count, N0=len(eta33_mid) + 2, levels=levels, nsteps=nsteps,
@@ -183,6 +185,7 @@ def converge_block_batched(p0, p1, eta33_mid, levels=6, nsteps=2048, scheme=None
         t0 = time.perf_counter()
         r = solver.solve(taus, Ls, eta0, want_fields=want_fields)
         r["seconds"] = time.perf_counter() - t0
+        r["seconds_make_sweep"] = t_ms
     finally:
         if own:
             solver.close()
