@@ -300,6 +300,102 @@ def parity_spot_check(run, count=8):
     return len(pts), float(worst)
 
 
+def mesh2d_leg(rank, world, local, torch, dist, scft_b200):
+    """Extra key "mesh2d": the 2-D path (BASELINE.json configs[3], [4]; pcg2d.cu) — Q1 mesh, assembled sliced-ELL matrices,
+    Jacobi-PCG per contour step, implicit Euler.
+      * 1M DOFs (nx=1024, ny=1023 cells), n=2048: one full residual evaluation of a y-modulated field, sharded in x-slabs
+        over the ranks (peer-memory persistent kernel at N > 1), CUDA-event time of the march, max over ranks.
+      * N = 1 only: the same mesh with a y-invariant field against the 1-D engine (parity at configuration scale).
+      * 16.8M DOFs (4095 x 4095 cells): microseconds per CG iteration with the iteration count per step capped
+        (16 steps x 50 iterations: the per-iteration work is that of the real solve; the fields are not used)."""
+    dev = torch.device("cuda", local)
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "ref_fixtures.npz"))
+    L = scft_b200.L_REF
+
+    def nccl_id():
+        if world == 1:
+            return None
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt = torch.tensor(list(scft_b200.nccl_unique_id()), dtype=torch.uint8, device=dev)
+        dist.broadcast(idt, 0)
+        return bytes(idt.cpu().tolist())
+
+    def attach(eng):
+        hb = torch.tensor(list(eng.p2p_handle()), dtype=torch.uint8, device=dev)
+        allh = [torch.zeros_like(hb) for _ in range(world)]
+        dist.all_gather(allh, hb)
+        eng.p2p_attach(b"".join(bytes(h.cpu().tolist()) for h in allh))
+        dist.barrier()
+
+    def run(nx, ny, n, eta, maxit=0, mode="p2p", reps=2):
+        eng = scft_b200.Engine2D(nx, ny, L=L, Ly=L * ny / nx, nsteps=n, rtol=1e-12, maxit=maxit, device=local, rank=rank,
+                                 world=world, nccl_id=nccl_id())
+        if world > 1 and mode == "p2p":
+            attach(eng)
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            out = eng.residual(eta)
+        it, ms = eng.stats()
+        phi = eng.phi()
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if mode == "p2p":
+                eng.p2p_detach()
+            dist.barrier()
+        rows = (eng.row0, eng.nrows)
+        eng.close()
+        if world > 1:
+            dist.barrier()
+        return float(t[0]), it, phi, out, rows
+
+    res = {"scheme": "implicit Euler on the deal.II matrices A, B, C (scft.cc:643-656), Jacobi-PCG per step, rtol 1e-12",
+           "bytes_per_dof_per_cg_iteration": 228}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+    # ---- 1M DOFs, n = 2048, full evaluation
+    nx, ny, n = 1024, 1023, NSTEPS
+    x = L * np.arange(nx + 1) / nx
+    eta_x = np.interp(x, fx["res1024_xl"] * L, fx["res1024_eta"])
+    y = np.arange(ny + 1) / ny
+    eta = (eta_x[:, None] * (1 + 0.1 * np.cos(2 * np.pi * y)[None, :])).ravel()
+    ms, it, phi, out, rows = run(nx, ny, n, eta, reps=1 if world == 1 else 2)
+    ndof = (nx + 1) * (ny + 1)
+    res["dofs_1m"] = {"mesh_cells": [nx, ny], "dofs": ndof, "nsteps": n, "march_ms": ms, "cg_iterations": it,
+                      "cg_iterations_per_step": it / n, "us_per_cg_iteration": ms * 1e3 / it,
+                      "dof_steps_per_s": ndof * n / (ms * 1e-3),
+                      "hbm_frac_per_gpu": 228.0 * ndof / world * it / (ms * 1e-3) / 1e9 / peak,
+                      "exchange": "none (one GPU)" if world == 1 else "peer-memory persistent kernel (halo stores + in-kernel all-reduce over NVLink)"}
+    if world == 1:
+        # parity at configuration scale: y-invariant field == 1-D engine (SURVEY.md section 8d item 4)
+        e1 = scft_b200.Engine(nx + 1, nsteps=n, scheme=scft_b200.IE_CONSISTENT, device=local)
+        em = np.interp(x, fx["res1024_xl"] * L, fx["res1024_eta"])[1:-1]
+        e1.residual(em)
+        phi1, ef = e1.phi(), e1.eta_full()
+        e1.close()
+        ms2, it2, phi2, _, _ = run(nx, ny, n, np.repeat(ef, ny + 1), reps=1)
+        phi2 = phi2.reshape(nx + 1, ny + 1)
+        res["dofs_1m"]["parity_y_invariant_vs_1d_engine"] = {
+            "max_abs_err_phi": float(np.abs(phi2 - phi1[:, None]).max()), "tolerance": 1e-10,
+            "cg_iterations": it2, "march_ms": ms2}
+    # ---- 16.8M DOFs, per-iteration cost
+    nx = ny = 4095
+    x = L * np.arange(nx + 1) / nx
+    eta_x = np.interp(x, fx["res1024_xl"] * L, fx["res1024_eta"])
+    y = np.arange(ny + 1) / ny
+    eta = (eta_x[:, None] * (1 + 0.1 * np.cos(2 * np.pi * y)[None, :])).ravel()
+    ndof = (nx + 1) * (ny + 1)
+    big = {"mesh_cells": [nx, ny], "dofs": ndof, "nsteps": 16, "cg_iterations_per_step_cap": 50}
+    for mode in (["one_gpu"] if world == 1 else ["p2p", "nccl"]):
+        ms, it, _, _, _ = run(nx, ny, 16, eta, maxit=50, mode=mode, reps=2)
+        big[mode] = {"march_ms": ms, "cg_iterations": it, "us_per_cg_iteration": ms * 1e3 / it,
+                     "hbm_frac_per_gpu": 228.0 * ndof / world / (ms * 1e-3 / it) / 1e9 / peak}
+    res["dofs_16m"] = big
+    return res
+
+
 def main():
     # stdout carries exactly ONE line (the JSON); anything libraries print (e.g. NCCL's version banner) goes to stderr
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -314,6 +410,7 @@ def main():
     ap.add_argument("--problems", type=int, default=TOTAL_PROBLEMS, help="problems of the whole sweep (sharded over the ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling leg at N > 1")
+    ap.add_argument("--no-mesh2d", action="store_true", help="skip the extra 2-D mesh leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -407,6 +504,14 @@ def main():
                 "ms_per_step": wms / args.steps, "march_kernel_ms": wmarch,
                 "hbm_frac_per_gpu": TOTAL_PROBLEMS * ni * NSTEPS * BYTES_PER_DOF_STEP / (wmarch * 1e-3) / 1e9}
 
+    # ---- extra: the 2-D mesh path (configs[3], [4]); a failure here must not take the headline line down
+    mesh2d = None
+    if not args.no_mesh2d:
+        try:
+            mesh2d = mesh2d_leg(rank, world, local, torch, dist, scft_b200)
+        except Exception as exc:   # noqa: BLE001
+            mesh2d = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         assert allres.shape[0] == total
         finite = int(np.isfinite(allres[:, 0]).sum())
@@ -468,6 +573,8 @@ def main():
                              "bytes_per_dof_step": BYTES_PER_DOF_STEP}}
         if weak:
             line["weak"] = weak
+        if mesh2d:
+            line["mesh2d"] = mesh2d
         assert max_rel_all < 1e-10, f"GPU results differ from the oracle: {max_rel_all:.3e}"
         if not args.no_cpu_baseline and world == 1:
             cores = host_cores()

@@ -79,3 +79,22 @@ def test_y_invariant_field_equals_1d_engine(sb, fixtures):
     assert np.abs(phi2 - phi2[:, [0]]).max() < 1e-11
     assert np.abs(phi2[:, 0] - phi1).max() < REL
     e1.close(); e2.close()
+
+
+def test_y_invariant_field_equals_1d_engine_at_config_scale(sb, fixtures):
+    """BASELINE.json configs[3] scale: 1024 x 1023 cells (1.05M DOFs), n = 2048 implicit-Euler steps, y-invariant field from the
+    m=1024 spectral result: the 2-D density must equal the 1-D engine's (IE on the consistent matrices) to 1e-10 on every node"""
+    nx, ny, n = 1024, 1023, 2048
+    e1 = sb.Engine(nx + 1, nsteps=n, scheme=sb.IE_CONSISTENT)
+    e1.residual(fixtures["res1024_eta"][1:-1])
+    phi1, ef = e1.phi(), e1.eta_full()
+    e1.close()
+    e2 = sb.Engine2D(nx, ny, nsteps=n, rtol=1e-12)
+    out = e2.residual(np.repeat(ef, ny + 1))
+    phi2 = e2.phi().reshape(nx + 1, ny + 1)
+    it, ms = e2.stats()
+    e2.close()
+    assert it >= n
+    assert np.abs(phi2 - phi2[:, [0]]).max() < 1e-11
+    assert np.abs(phi2[:, 0] - phi1).max() < REL
+    assert np.isfinite(out).all()
