@@ -53,6 +53,9 @@ struct Sys2D {
   int *col;                 // SELL: [nslices][9][32], LOCAL vector index (halo_left + owned + halo_right)
   double *valT, *valA;      // same layout
   double *dinv;             // [nrows] 1 / diag(T)
+  // matrix-free application (apply_row): element entries of A and of A + dt B by the relation of the two nodes inside a
+  // cell (0 same node, 1 x-neighbour, 2 y-neighbour, 3 diagonal), and dt hx hy / 144 for the (eta_h phi_a, phi_b) part
+  double eA[4], eT[4], cC;
 };
 
 struct Vec2D {
@@ -180,19 +183,53 @@ __device__ Part reduce_partials(const double *partial, int nblocks) {
   return t;
 }
 
+// Row `i` of T v (and of A v when WANT_A) WITHOUT reading the assembled matrix: the structured Q1 mesh makes the column
+// pattern implicit and the element matrices closed-form, so the 108 bytes per row of stored values and column indices are
+// replaced by 9 values of v and 9 values of eta, almost all of them L1/L2 hits.  Per cell (nodes [bx][by], row node a):
+//   ((A + dt B)_e v)_a = sum_b e(rel(a,b)) v_b                       constant element entries, Sys2D::eA / eT
+//   (C_e v)_a = (eta_h phi_a, sum_b v_b phi_b) with the 1-D triple products  int phi_a phi_b phi_k = h/4 (a=b=k), h/12 (else):
+//             = hx hy/144 [ (E0+E1)(V0+V1) + 2 (eta_0a+eta_1a)(v_0a+v_1a) + 2 E_ax V_ax + 4 eta_aa v_aa ],
+//     E_k = eta[k][0]+eta[k][1], V_b = v[b][0]+v[b][1]  — the exact integral, i.e. what the 2x2 Gauss rule of the assembly
+//     (scft.cc:610,653-655) evaluates, so matrix-free and assembled rows agree to rounding (tests).
+// Dirichlet columns: wall rows are identity rows of T and zero rows of A (scft.cc:599-606); the vectors this is applied to
+// (q, z) vanish on the wall nodes, so the wall columns need no masking.
+struct RowTA { double t, a; };
+template <bool PEER, bool WANT_A>
+__device__ __forceinline__ RowTA apply_row(const Sys2D &S, const double *__restrict__ v, int i) {
+  const int g = S.row0 + i, ix = g / S.nyp, iy = g - ix * S.nyp;
+  RowTA out = {0.0, 0.0};
+  auto val = [&](int o) -> double {   // entry o of v (owned part starts at 0, halos on either side)
+    if (PEER && (o < 0 || o >= S.nrows)) return __ldcv(v + o);
+    return v[o];
+  };
+  if (ix == 0 || ix == S.nx) { out.t = val(i); return out; }
+  const double *__restrict__ eta = S.eta + g;
+#pragma unroll
+  for (int ex = 0; ex < 2; ex++) {       // cell to the left (ex = 0) / right (ex = 1) of the row node
+#pragma unroll
+    for (int ey = 0; ey < 2; ey++) {     // cell below / above
+      if ((ey == 0 && iy == 0) || (ey == 1 && iy == S.ny)) continue;
+      const int dxo = (ex == 0 ? -S.nyp : S.nyp), dyo = (ey == 0 ? -1 : 1);
+      // the row node is node a of the cell; xo = its x-neighbour, yo = its y-neighbour, dd = the diagonal node
+      const double v_aa = val(i), v_xo = val(i + dxo), v_yo = val(i + dyo), v_dd = val(i + dxo + dyo);
+      const double e_aa = eta[0], e_xo = eta[dxo], e_yo = eta[dyo], e_dd = eta[dxo + dyo];
+      double t = fma(S.eT[0], v_aa, fma(S.eT[1], v_xo, fma(S.eT[2], v_yo, S.eT[3] * v_dd)));
+      const double Ea = e_aa + e_yo, Eo = e_xo + e_dd, Va = v_aa + v_yo, Vo = v_xo + v_dd;   // sums over y at the row node's x / the other x
+      const double c = fma(Ea + Eo, Va + Vo, fma(2.0 * (e_aa + e_xo), v_aa + v_xo, fma(2.0 * Ea, Va, 4.0 * e_aa * v_aa)));
+      out.t += fma(S.cC, c, t);
+      if (WANT_A) out.a += fma(S.eA[0], v_aa, fma(S.eA[1], v_xo, fma(S.eA[2], v_yo, S.eA[3] * v_dd)));
+    }
+  }
+  return out;
+}
+
 // start of a contour step: b = A q, initial guess x = q, r = b - T x, z = D^-1 r, p = w = 0; partial bb = b.b
 __device__ Part step_begin(const Sys2D &S, const Vec2D &V, int tid, int nthreads) {
   Part acc = {0, 0, 0, 0};
   for (int i = tid; i < S.nslices * 32; i += nthreads) {
     if (i >= S.nrows) continue;
-    double bq = 0.0, tq = 0.0;
-#pragma unroll
-    for (int k = 0; k < SLOTS; k++) {
-      const double qv = V.q[S.col[sell(i, k)] - S.halo + 0];   // q is stored like z (with halos), see host
-      bq = fma(S.valA[sell(i, k)], qv, bq);
-      tq = fma(S.valT[sell(i, k)], qv, tq);
-    }
-    const double r = bq - tq;
+    const RowTA ta = apply_row<false, true>(S, V.q, i);   // q is stored like z (with halos), see host
+    const double bq = ta.a, r = bq - ta.t;
     V.b[i] = bq; V.x[i] = V.q[i]; V.r[i] = r; V.z[i] = S.dinv[i] * r; V.p[i] = 0.0; V.w[i] = 0.0;
     acc.d = fma(bq, bq, acc.d);
   }
@@ -212,9 +249,7 @@ __device__ __forceinline__ double gather(const double *v, int c, const Sys2D &S)
 template <bool PEER = false>
 __device__ Part cg_spmv(const Sys2D &S, const Vec2D &V, int tid, int nthreads, int phase = 0) {
   Part acc = {0, 0, 0, 0};
-  // no aliasing between the matrix, the gathered vector and the output: lets the loads of the next rows issue early
-  const double *__restrict__ valT = S.valT;
-  const int *__restrict__ col = S.col;
+  // no aliasing between the gathered vector and the output: lets the loads of the next rows issue early
   const double *__restrict__ zv = V.z;
   const double *__restrict__ rv = V.r;
   double *__restrict__ sv_out = V.s;
@@ -225,9 +260,7 @@ __device__ Part cg_spmv(const Sys2D &S, const Vec2D &V, int tid, int nthreads, i
       const bool edge = (i < S.halo) || (i >= S.nrows - S.halo);
       if (edge != (phase == 2)) continue;
     }
-    double sv = 0.0;
-#pragma unroll
-    for (int k = 0; k < SLOTS; k++) sv = fma(valT[sell(i, k)], gather<PEER>(zv, col[sell(i, k)], S), sv);
+    const double sv = apply_row<PEER, false>(S, zv, i).t;
     sv_out[i] = sv;
     const double r = rv[i], z = zv[i];
     acc.a = fma(r, z, acc.a); acc.b = fma(z, sv, acc.b); acc.c = fma(r, r, acc.c);
@@ -277,7 +310,7 @@ __device__ void step_end(const March2D &M, int j, int tid, int nthreads) {
 
 // ------------------------------------------------------------------------------------------------
 // single GPU: the whole march in one persistent cooperative kernel
-__global__ void __launch_bounds__(TPB2, 5) march2d_persistent_kernel(March2D M) {
+__global__ void __launch_bounds__(TPB2, 4) march2d_persistent_kernel(March2D M) {
   cg::grid_group grid = cg::this_grid();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const Sys2D &S = M.S; const Vec2D &V = M.V;
@@ -425,7 +458,7 @@ __device__ Part allreduce_partials(const P2P &X, const double *partial, int nblo
   return t;
 }
 
-__global__ void __launch_bounds__(TPB2, 5) march2d_p2p_kernel(March2D M, P2P X, ull seq0, ull rseq0) {
+__global__ void __launch_bounds__(TPB2, 4) march2d_p2p_kernel(March2D M, P2P X, ull seq0, ull rseq0) {
   cg::grid_group grid = cg::this_grid();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const Sys2D &S = M.S; const Vec2D &V = M.V;
@@ -446,14 +479,8 @@ __global__ void __launch_bounds__(TPB2, 5) march2d_p2p_kernel(March2D M, P2P X, 
     Part pb = {0, 0, 0, 0};
     for (int i = tid; i < S.nslices * 32; i += nthreads) {
       if (i >= S.nrows) continue;
-      double bq = 0.0, tq = 0.0;
-#pragma unroll
-      for (int k = 0; k < SLOTS; k++) {
-        const double qv = gather<true>(V.q, S.col[sell(i, k)], S);
-        bq = fma(S.valA[sell(i, k)], qv, bq);
-        tq = fma(S.valT[sell(i, k)], qv, tq);
-      }
-      const double r = bq - tq, z = S.dinv[i] * r;
+      const RowTA ta = apply_row<true, true>(S, V.q, i);
+      const double bq = ta.a, r = bq - ta.t, z = S.dinv[i] * r;
       V.b[i] = bq; V.x[i] = V.q[i]; V.r[i] = r; V.z[i] = z; V.p[i] = 0.0; V.w[i] = 0.0;
       if (push_boundary(S, X, X.off_z, i, z)) __threadfence_system();
       pb.d = fma(bq, bq, pb.d);
@@ -703,6 +730,13 @@ int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_en
   Sys2D &S = e->M.S;
   S.nx = nx; S.ny = ny; S.nyp = nyp; S.row0 = e->ix0 * nyp; S.nrows = e->nrows; S.halo = e->halo; S.nslices = e->nslices;
   S.hx = cfg->L / nx; S.hy = cfg->Ly / ny; S.dt = 1.0 / n;
+  {
+    const double hx = S.hx, hy = S.hy, m = hx * hy / 36.0;
+    const double eB[4] = {hy / (3 * hx) + hx / (3 * hy), -hy / (3 * hx) + hx / (6 * hy), hy / (6 * hx) - hx / (3 * hy), -hy / (6 * hx) - hx / (6 * hy)};
+    const double mA[4] = {4 * m, 2 * m, 2 * m, m};
+    for (int k = 0; k < 4; k++) { S.eA[k] = mA[k]; S.eT[k] = mA[k] + S.dt * eB[k]; }
+    S.cC = S.dt * hx * hy / 144.0;
+  }
   CK2(cudaMalloc(&S.col, sizeof(int) * nv));
   CK2(cudaMalloc(&S.valT, sizeof(double) * nv));
   CK2(cudaMalloc(&S.valA, sizeof(double) * nv));

@@ -23,4 +23,4 @@ for rep in range(2):
 ndof = (nx + 1) * (ny + 1)
 print(f"mesh {nx}x{ny} ({ndof} DOFs), {n} steps: march {ms:.1f} ms (wall {wall*1e3:.1f}), {it} CG iterations = {it/n:.1f}/step, "
       f"{ms*1e3/it:.2f} us/iteration, {ndof*n/(ms*1e-3):.3e} DOF-steps/s, "
-      f"{220*ndof*it/(ms*1e-3)/1e9:.0f} GB/s at 220 B/DOF/iteration")
+      f"{128*ndof*it/(ms*1e-3)/1e9:.0f} GB/s at 128 B/DOF/iteration (matrix-free rows)")
