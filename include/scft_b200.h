@@ -249,6 +249,9 @@ int scftb_refine_mesh_adaptive(int N, const double *x, const double *eta_mid, do
 /* solution_yita_1D_N=<N>.txt writer (scft.cc:319-337) and reader (read_yita_middle_1D, scft_util.cc:13-41) */
 int scftb_write_solution(const char *path, int N, double err, double F, const double *x, const double *eta_full);
 int scftb_read_solution(const char *path, int *N, double *x, double *eta, int capacity);
+/* detailedsolution_yita_1D_N=<N>.txt (scft.cc:269-312): eta_h sampled on nplot equidistant points (<= 1: 2^18 + 1) */
+int scftb_write_detailed_solution(const char *path, int N, double err, double F, const double *x, const double *eta_full,
+                                  int nplot);
 /* Exp_m*_n2048_IE.res reader (1D_FEM.c:322-342): rows of x/l, phi, eta after 9 header lines */
 int scftb_read_res(const char *path, int rows, double *xl, double *phi, double *eta);
 

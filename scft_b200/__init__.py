@@ -7,5 +7,5 @@ there is no CPU fallback.
 """
 from .engine import (Engine, lib, IE_ROWSCALE, IE_CONSISTENT, IRK4_CONSISTENT, QUAD_ROMBERG,  # noqa: F401
                      QUAD_TRAPEZOID, TAU_REF, L_REF, ScftError, launch_count, LIB_PATH, AndersonBatch,
-                     spline, refine_mesh, refine_mesh_adaptive, write_solution, read_solution, read_res, Engine2D, nccl_unique_id,
+                     spline, refine_mesh, refine_mesh_adaptive, write_solution, write_detailed_solution, read_solution, read_res, Engine2D, nccl_unique_id,
                      PrecondAndersonBatch, padm_batch, free_energy_weights, SweepSolver)

@@ -81,7 +81,9 @@ void f0_given(int N, const double *x, double tau, double *f0) {
 // ---------------------------------------------------------------------------------------------
 // natural-spline wall values on a NON-uniform mesh (scft.cc:452-490, spline_chen.c:12-106 with
 // m = 0): the reference solves the tridiagonal system densely with gaussj; here one thread per
-// problem runs Thomas over the N-2 knots.  Uniform meshes never need this (see eta_node()).
+// problem runs Thomas over the N-2 knots, its two sweep arrays interleaved across the problems of the
+// launch (element i of problem p at [i*nprob + p]) so that a warp's scratch accesses are contiguous.
+// Uniform meshes never need this (see eta_node()).
 // ---------------------------------------------------------------------------------------------
 __global__ void spline_bnd_kernel(int nprob, int N, const double *x, const double *eta_mid, long long eta_stride,
                                   double *scratch, double *eta_bnd, int pshare) {
@@ -91,19 +93,21 @@ __global__ void spline_bnd_kernel(int nprob, int N, const double *x, const doubl
   x += (size_t)(pshare ? 0 : p) * N;         // mesh of this problem (pshare: every problem on the mesh of slot 0)
   const double *xk = x + 1;                  // knots = interior nodes
   const double *y = eta_mid + (size_t)p * eta_stride;
-  double *cp = scratch + (size_t)p * 2 * Nx, *dp = cp + Nx;
+  const size_t S = nprob;
+  double *cp = scratch + p, *dp = scratch + (size_t)Nx * S + p;
   // rows i=1..Nx-2: (x_i-x_{i-1})/6, (x_{i+1}-x_{i-1})/3, (x_{i+1}-x_i)/6 ; rows 0, Nx-1: M = 0
-  cp[0] = 0.0; dp[0] = 0.0;
+  double cprev = 0.0, dprev = 0.0;
   for (int i = 1; i < Nx - 1; i++) {
     double lo = (xk[i] - xk[i - 1]) / 6., di = (xk[i + 1] - xk[i - 1]) / 3., up = (xk[i + 1] - xk[i]) / 6.;
     double rhs = (y[i + 1] - y[i]) / (xk[i + 1] - xk[i]) - (y[i] - y[i - 1]) / (xk[i] - xk[i - 1]);
-    double den = di - lo * cp[i - 1];
-    cp[i] = up / den;
-    dp[i] = (rhs - lo * dp[i - 1]) / den;
+    double den = di - lo * cprev;
+    cprev = up / den;
+    dprev = (rhs - lo * dprev) / den;
+    cp[i * S] = cprev; dp[i * S] = dprev;
   }
   double Mn = 0.0, M1 = 0.0, Mlast1 = 0.0;
   for (int i = Nx - 2; i >= 1; i--) {
-    Mn = dp[i] - cp[i] * Mn;
+    Mn = dp[i * S] - cp[i * S] * Mn;
     if (i == Nx - 2) Mlast1 = Mn;
     if (i == 1) M1 = Mn;
   }

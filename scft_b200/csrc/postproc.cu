@@ -135,6 +135,28 @@ int scftb_write_solution(const char *path, int N, double err, double F, const do
   return SCFTB_OK;
 }
 
+// detailedsolution_yita_1D_N=<N>.txt (scft.cc:269-312): the piecewise-linear eta_h (FEFieldFunction on the Q1 mesh,
+// scft.cc:280-281) sampled on nplot = 2^18 + 1 equidistant points of [0, L], same three-part layout as the solution file
+int scftb_write_detailed_solution(const char *path, int N, double err, double F, const double *x, const double *eta_full, int nplot) {
+  if (!path || N < 2 || !x || !eta_full) return fail(SCFTB_ERR_ARG, "write_detailed_solution: bad argument");
+  if (nplot <= 1) nplot = (1 << 18) + 1;   // scft.cc:271
+  FILE *fp = fopen(path, "w+");
+  if (!fp) return fail(SCFTB_ERR_ARG, std::string("cannot create file ") + path);
+  fprintf(fp, "N= %d, ", N);
+  fprintf(fp, "ERROR= %e \n", err);
+  fprintf(fp, "mean_field_free_energy, %2.15f \n", F);
+  const double L = x[N - 1];
+  int k = 0;
+  for (int i = 0; i < nplot; i++) {
+    const double xp = L * i / (nplot - 1);
+    while (k < N - 2 && xp > x[k + 1]) k++;
+    const double t = (xp - x[k]) / (x[k + 1] - x[k]);
+    fprintf(fp, "%i,%2.15f,%2.15f\n", i, xp, (1 - t) * eta_full[k] + t * eta_full[k + 1]);
+  }
+  fclose(fp);
+  return SCFTB_OK;
+}
+
 // reader of the same format (scft_util.cc:13-41); pass x = eta = NULL to query N only
 int scftb_read_solution(const char *path, int *N, double *x, double *eta, int capacity) {
   FILE *fp = fopen(path, "r");

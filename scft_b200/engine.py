@@ -57,7 +57,7 @@ EXPORTS = ["scftb_create", "scftb_destroy", "scftb_last_error", "scftb_launch_co
            "scftb_set_diblock", "scftb_residual_ab", "scftb_residual_ab_batch", "scftb_get_phi_ab", "scftb_callback_ab_c0",
            "scftb_mixer_create", "scftb_mixer_destroy", "scftb_mixer_reset", "scftb_mixer_iterate_device",
            "scftb_mixer_status", "scftb_mixer_get_x", "scftb_mixer_get_y", "scftb_get_slots", "scftb_get_kernel_name", "scftb_mixer_set_freeze", "scftb_set_timing", "scftb_get_march_ms", "scftb_spline", "scftb_refine_mesh", "scftb_refine_mesh_adaptive", "scftb_write_solution",
-           "scftb_read_solution", "scftb_read_res", "scftb2d_nccl_unique_id", "scftb2d_create", "scftb2d_destroy",
+           "scftb_read_solution", "scftb_write_detailed_solution", "scftb_read_res", "scftb2d_nccl_unique_id", "scftb2d_create", "scftb2d_destroy",
            "scftb2d_rows", "scftb_pmixer_create", "scftb_pmixer_destroy", "scftb_pmixer_reset", "scftb_pmixer_iterate_device",
            "scftb_pmixer_status", "scftb_pmixer_get_x", "scftb_padm_batch", "scftb_refine_uniform_batch_device",
            "scftb_free_energy_weights", "scftb_sweep_create", "scftb_sweep_destroy", "scftb_sweep_target_N", "scftb_sweep_solve",
@@ -118,6 +118,7 @@ def lib():
         L.scftb_refine_mesh_adaptive.argtypes = [C.c_int, _dp, _dp, C.c_double, _ip, _dp, _dp]
         L.scftb_write_solution.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_double, _dp, _dp]
         L.scftb_read_solution.argtypes = [C.c_char_p, _ip, _dp, _dp, C.c_int]
+        L.scftb_write_detailed_solution.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_double, _dp, _dp, C.c_int]
         L.scftb_read_res.argtypes = [C.c_char_p, C.c_int, _dp, _dp, _dp]
         L.scftb_pmixer_create.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.POINTER(C.c_void_p)]
         L.scftb_pmixer_destroy.argtypes = [C.c_void_p]
@@ -475,6 +476,11 @@ def refine_mesh_adaptive(x, eta_mid, factor=10.0):
 def write_solution(path, err, F, x, eta_full):
     x, eta_full = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(eta_full, dtype=np.float64)
     _chk(lib().scftb_write_solution(path.encode(), len(x), err, F, _p(x), _p(eta_full)))
+
+
+def write_detailed_solution(path, err, F, x, eta_full, nplot=0):
+    x, eta_full = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(eta_full, dtype=np.float64)
+    _chk(lib().scftb_write_detailed_solution(path.encode(), len(x), err, F, _p(x), _p(eta_full), nplot))
 
 
 def read_solution(path):

@@ -30,6 +30,7 @@ static double now() {
 int main(int argc, char **argv) {
   std::string flow = "dealii", input, solver = "broydn", scheme_s = "irk4", outdir = ".";
   int levels = 1, nsteps = 2048, device = 0;
+  bool recheck = false, detailed = false;
   double tol = -1, tau = 5.30252230020752e-01, L = 3.72374357332160;  // drivescft.cc:269
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -44,11 +45,14 @@ int main(int argc, char **argv) {
     else if (a == "--L") L = atof(next().c_str());
     else if (a == "--outdir") outdir = next();
     else if (a == "--device") device = atoi(next().c_str());
+    else if (a == "--recheck") recheck = true;     // redoFxandshowError.cc:272-290: evaluate a saved solution, report max|F|, rewrite the files
+    else if (a == "--detailed") detailed = true;   // also write detailedsolution_yita_1D_N=<N>.txt (scft.cc:293-312), 2^18+1 rows
     else input = a;
   }
   if (input.empty()) {
     fprintf(stderr, "usage: drivescft_b200 <N=33_for_read.txt | Exp_m32_n2048_IE.res> [--flow dealii|1dfem] "
-                    "[--scheme irk4|ie|ie_rowscale] [--solver broydn|broydn_dev|adm_chen] [--levels K] [--nsteps n] [--tol t]\n");
+                    "[--scheme irk4|ie|ie_rowscale] [--solver broydn|broydn_dev|adm_chen|adm|padm] [--levels K] [--nsteps n] [--tol t] "
+                    "[--recheck] [--detailed]\n");
     return 2;
   }
   int scheme = scheme_s == "irk4" ? SCFTB_IRK4_CONSISTENT : (scheme_s == "ie" ? SCFTB_IE_CONSISTENT : SCFTB_IE_ROWSCALE);
@@ -81,7 +85,15 @@ int main(int argc, char **argv) {
     std::vector<double> xm(eta.begin() + 1, eta.end() - 1), res(n);
     double t0 = now();
     int check = 1, rc = 0;
-    if (solver == "broydn") {
+    if (recheck) {               // no solve: the saved field is evaluated as it is
+      check = 0;
+    } else if (solver == "padm") {      // preconditioned Anderson mixing (pmixer.cu)
+      rc = scftb_padm_batch(e, 1, xm.data(), tol, 400, 10, nullptr, nullptr);
+      check = rc == SCFTB_OK ? 0 : 1;
+    } else if (solver == "adm") {       // adm.c semantics on the device (fixed TOLF = 1e-10)
+      rc = scftb_adm_batch(e, 1, xm.data(), 100000, nullptr, nullptr);
+      check = rc == SCFTB_OK ? 0 : 1;
+    } else if (solver == "broydn") {
       double err = tol;
       int jc = 0;
       rc = scftb_broydn(scftb_callback_c0, xm.data(), n, &check, &err, &jc);
@@ -100,7 +112,7 @@ int main(int argc, char **argv) {
       }
       check = rc == SCFTB_OK ? 0 : 1;
     }
-    if (rc != SCFTB_OK && rc != SCFTB_ERR_NOCONV) { fprintf(stderr, "solver failed: %s\n", scftb_last_error()); return 1; }
+    if (rc != SCFTB_OK && rc != SCFTB_ERR_NOCONV && rc != SCFTB_ERR_NAN) { fprintf(stderr, "solver failed: %s\n", scftb_last_error()); return 1; }
     double t_solve = now() - t0;
     // print_and_save_yita_1D (scft.cc:246-339): residual of the final field, free energy, result file
     CHECK(scftb_residual(e, xm.data(), res.data()));
@@ -114,6 +126,11 @@ int main(int argc, char **argv) {
     char path[512];
     snprintf(path, sizeof path, "%s/solution_yita_1D_N=%03d.txt", outdir.c_str(), N);
     CHECK(scftb_write_solution(path, N, emax, F, x.data(), full.data()));
+    if (detailed) {
+      char dpath[512];
+      snprintf(dpath, sizeof dpath, "%s/detailedsolution_yita_1D_N=%03d.txt", outdir.c_str(), N);
+      CHECK(scftb_write_detailed_solution(dpath, N, emax, F, x.data(), full.data(), 0));
+    }
     printf("level %d: N=%d check=%d Error= %e mean_field_free_energy=%2.15f Q=%2.15f solve_time=%.3fs -> %s\n", level, N, check,
            emax, F, Q, t_solve, path);
     fflush(stdout);

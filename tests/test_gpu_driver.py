@@ -71,3 +71,34 @@ def test_1dfem_flow(sb, fixtures, tmp_path):
             fh.write(f" {a:.6e}  {b:.14e}  {c:.14e}  0.0  0.0\n")
     rows = run_driver([res, "--flow", "1dfem", "--outdir", str(tmp_path)])
     assert rows[0]["N"] == 33 and rows[0]["err"] < 1e-7     # broydn err = 1e-8 (1D_FEM.c:350)
+
+
+def test_recheck_mode_reproduces_reference_file_error(sb, fixtures, tmp_path):
+    """redoFxandshowError.cc:272-290: re-evaluate a saved solution and rewrite its files.  On the reference's own
+    N=33_for_read.txt the driver must report the residual recorded in that file's header (1.42e-9) and its free energy,
+    and write the detailed 2^18+1-point file (scft.cc:293-312)."""
+    inp = str(tmp_path / "N=33_for_read.txt")
+    sb.write_solution(inp, float(fixtures["n33_error"]), float(fixtures["n33_F"]), fixtures["n33_x"], fixtures["n33_eta"])
+    rows = run_driver([inp, "--flow", "dealii", "--scheme", "irk4", "--recheck", "--detailed", "--outdir", str(tmp_path)])
+    assert len(rows) == 1 and rows[0]["N"] == 33
+    assert rows[0]["err"] < 2e-9 and rows[0]["F"] == pytest.approx(float(fixtures["n33_F"]), abs=1e-12)
+    det = open(str(tmp_path / "detailedsolution_yita_1D_N=033.txt")).read().splitlines()
+    assert len(det) == 2 + (1 << 18) + 1 and det[0].startswith("N= 33, ERROR=")
+    i, xv, ev = det[2 + (1 << 17)].split(",")
+    assert int(i) == 1 << 17 and float(xv) == pytest.approx(sb.L_REF / 2, abs=1e-12)
+    assert float(ev) == pytest.approx(np.interp(sb.L_REF / 2, fixtures["n33_x"], fixtures["n33_eta"]), abs=2e-9)
+
+
+def test_dealii_flow_preconditioned_mixing_to_m1024(sb, oracle, fixtures, tmp_path):
+    """BASELINE.json configs[1]: the m=1024, n=2048 implicit-Euler hard-surface problem converged by Anderson mixing
+    (preconditioned, pmixer.cu) through the reference's refinement flow; the final file re-evaluates on the oracle."""
+    inp = str(tmp_path / "N=33_for_read.txt")
+    sb.write_solution(inp, float(fixtures["n33_error"]), float(fixtures["n33_F"]), fixtures["n33_x"], fixtures["n33_eta"])
+    rows = run_driver([inp, "--flow", "dealii", "--scheme", "ie_rowscale", "--solver", "padm", "--levels", "6", "--tol", "1e-9",
+                       "--outdir", str(tmp_path)])
+    assert [r["N"] for r in rows] == [33, 65, 129, 257, 513, 1025]
+    assert all(r["check"] == 0 and r["err"] < 1e-9 for r in rows)
+    x, eta = sb.read_solution(str(tmp_path / "solution_yita_1D_N=1025.txt"))
+    ref = oracle.residual(oracle.eta_full(x, eta[1:-1]), oracle.f0_given(x), scheme=oracle.IE_ROWSCALE, nsteps=2048)
+    assert np.abs(ref["out"]).max() < 2e-9       # the file keeps 15 decimals of eta
+    assert rows[-1]["F"] == pytest.approx(0.001909977319, abs=2e-11)   # device Broyden's value, profiles/r1_continuation_m1024.txt

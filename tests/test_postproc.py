@@ -120,3 +120,19 @@ def test_adaptive_refinement_reproduces_the_prototypes_own_mesh(sb, fixtures):
     xn, en = sb.refine_mesh_adaptive(x, eta[1:-1])
     assert len(xn) == 43 and np.abs(xn - fixtures["matlab43_x"]).max() < 1e-12
     assert len(en) == 41 and np.all(np.isfinite(en))
+
+
+def test_detailed_solution_file_layout(sb, tmp_path):
+    """detailedsolution_yita_1D_N=<N>.txt (scft.cc:293-312): header as the solution file, then i,x_i,eta_h(x_i) on
+    equidistant points with eta_h piecewise linear on the mesh (FEFieldFunction on Q1)"""
+    x = np.array([0.0, 0.5, 1.5, 2.0])
+    eta = np.array([1.0, 3.0, -1.0, 0.0])
+    path = str(tmp_path / "detailedsolution_yita_1D_N=004.txt")
+    sb.write_detailed_solution(path, 1.5e-9, 0.00194, x, eta, nplot=9)
+    lines = open(path).read().splitlines()
+    assert lines[0] == "N= 4, ERROR= 1.500000e-09 " and lines[1] == "mean_field_free_energy, 0.001940000000000 "
+    assert len(lines) == 2 + 9
+    xs = np.array([float(ln.split(",")[1]) for ln in lines[2:]])
+    vs = np.array([float(ln.split(",")[2]) for ln in lines[2:]])
+    assert np.allclose(xs, np.linspace(0, 2, 9), atol=1e-15) and np.allclose(vs, np.interp(xs, x, eta), atol=1e-14)
+    assert lines[2].startswith("0,0.000000000000000,1.000000000000000")
