@@ -126,7 +126,8 @@ int ensure_kernel(scftb_engine *e, DiblockState *s) {
   return SCFTB_OK;
 }
 
-int launch_ab(scftb_engine *e, DiblockState *s, int nprob, const double *d_w, double *d_out, cudaStream_t st, bool pshare = false) {
+int launch_ab(scftb_engine *e, DiblockState *s, int nprob, const double *d_w, double *d_out, cudaStream_t st, bool pshare = false,
+              long long w_stride = 0, long long out_stride = 0, const int *d_skip = nullptr) {
   int rc = ensure_kernel(e, s);
   if (rc) return rc;
   if (s->chi_dirty) {
@@ -137,7 +138,8 @@ int launch_ab(scftb_engine *e, DiblockState *s, int nprob, const double *d_w, do
   P.N = e->cfg.N; P.ni = e->ni; P.nsteps = e->cfg.nsteps;
   P.scheme = e->cfg.scheme; P.nprob = nprob; P.store_full = 0;
   P.uniform = e->uniform ? 1 : 0; P.sign = e->cfg.sign; P.pshare = pshare ? 1 : 0;
-  P.eta_mid = d_w; P.eta_stride = 2 * (long long)e->ni; P.out_stride = 2 * (long long)e->ni; P.skip = nullptr;
+  P.eta_mid = d_w; P.eta_stride = w_stride ? w_stride : 2 * (long long)e->ni;
+  P.out_stride = out_stride ? out_stride : 2 * (long long)e->ni; P.skip = d_skip;
   P.f0 = e->d_f0; P.L = e->d_L; P.x = e->d_x; P.eta_bnd = e->d_eta_bnd; P.w = e->d_w;
   P.hist = s->d_hist; P.hist_stride = (long long)(e->cfg.nsteps + 1) * (long long)s->SL;
   P.out = d_out; P.phi = e->d_phi; P.Q = e->d_Q; P.eta_full = nullptr;
@@ -208,6 +210,17 @@ int residual_ab_batch_shared(scftb_engine *e, int nprob, const double *w, double
 extern "C" {
 
 int scftb_residual_ab(scftb_engine *e, const double *w, double *out) { return scftb_residual_ab_batch(e, 1, w, out); }
+}  // extern "C"
+namespace scftb {
+// device-pointer launch with caller strides and skip flags, for the device-resident mixers (mixer.cu)
+int launch_residual_ab(scftb_engine *e, int nprob, const double *d_w, long long w_stride, double *d_out, long long out_stride,
+                       const int *d_skip, cudaStream_t st) {
+  DiblockState *s = (DiblockState *)e->diblock_state;
+  if (!s) return fail(SCFTB_ERR_STATE, "scftb_set_diblock has not been called on this engine");
+  return launch_ab(e, s, nprob, d_w, d_out, st, false, w_stride, out_stride, d_skip);
+}
+}  // namespace scftb
+extern "C" {
 
 int scftb_get_phi_ab(scftb_engine *e, int p, double *phiA, double *phiB) {
   if (!e || p < 0 || p >= e->cfg.max_batch || !phiA || !phiB) return fail(SCFTB_ERR_ARG, "bad argument");

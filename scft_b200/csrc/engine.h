@@ -85,6 +85,10 @@ int launch_march(scftb_engine *e, int nprob, const double *d_eta, long long eta_
 // host-buffer batch of nprob fields of problem 0 (pshare launch), for the host-flow solvers
 int residual_batch_shared(scftb_engine *e, int nprob, const double *eta_mid, double *out);
 int residual_ab_batch_shared(scftb_engine *e, int nprob, const double *w, double *out);
+int launch_residual_ab(scftb_engine *e, int nprob, const double *d_w, long long w_stride, double *d_out, long long out_stride,
+                       const int *d_skip, cudaStream_t st);
+// unknowns per problem: N-2 (one species) or 2(N-2) (after scftb_set_diblock: eta_A, eta_B)
+inline int unknowns(const scftb_engine *e) { return e->diblock_state ? 2 * e->ni : e->ni; }
 int upload_params(scftb_engine *e);
 // order a march launch on `st` after the engine's previous march launch (no-op on the same stream) / note it
 int order_before_launch(scftb_engine *e, cudaStream_t st);

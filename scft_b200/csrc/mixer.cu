@@ -234,7 +234,7 @@ using namespace scftb;
 struct scftb_mixer {
   scftb_engine *e;
   int adm = 0;
-  int nprob, nn, nm, R, Final, k, freeze;
+  int nprob, nn, nm, R, Final, k, freeze, n;
   double lmd, tol;
   double *X, *Y, *xfinal, *lk, *err;
   int *k_restart, *done, *iters;
@@ -257,10 +257,11 @@ int scftb_mixer_create(scftb_engine *e, int nprob, double tol, double lmd, int n
   if (!e || !out || nprob < 1 || nprob > e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "mixer: bad argument");
   if (nn < 0 || nn > AND_NN_MAX) return fail(SCFTB_ERR_ARG, "mixer: mixing window nn must be in [0, 50]");
   scftb_mixer *m = new scftb_mixer();
-  m->e = e; m->nprob = nprob; m->nn = nn; m->nm = std::min(nn, e->ni); m->R = m->nm + 2;
+  m->e = e; m->nprob = nprob; m->nn = nn; m->nm = std::min(nn, unknowns(e)); m->R = m->nm + 2;
+  m->n = unknowns(e);   // a two-species engine (scftb_set_diblock called before) mixes (eta_A, eta_B) as one vector
   m->Final = Final; m->k = 0; m->lmd = lmd; m->tol = tol; m->freeze = 1;
   m->X = m->Y = m->xfinal = m->lk = m->err = nullptr; m->k_restart = m->done = m->iters = nullptr;
-  const size_t n = e->ni, ring = (size_t)nprob * m->R * n;
+  const size_t n = m->n, ring = (size_t)nprob * m->R * n;
   CK(cudaSetDevice(e->cfg.device));
 #define CKM(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { int rc = fail(SCFTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); scftb_mixer_destroy(m); return rc; } } while (0)
   CKM(cudaMalloc(&m->X, sizeof(double) * ring));
@@ -305,7 +306,8 @@ int scftb_mixer_reset(scftb_mixer *m, const double *x, int device, void *stream)
   scftb_engine *e = m->e;
   CK(cudaSetDevice(e->cfg.device));
   cudaStream_t st = device ? (cudaStream_t)stream : e->stream;
-  const size_t n = e->ni;
+  const size_t n = m->n;
+  if ((int)n != unknowns(e)) return fail(SCFTB_ERR_STATE, "mixer: the engine changed between one and two species after the mixer was created");
   CK(cudaMemcpy2DAsync(m->X, sizeof(double) * m->R * n, x, sizeof(double) * n, sizeof(double) * n, m->nprob,
                        device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   std::vector<double> lk(m->nprob, m->lmd);
@@ -329,12 +331,13 @@ int scftb_mixer_iterate_device(scftb_mixer *m, void *stream) {
     if (rc) return rc;
     CK(cudaStreamSynchronize(e->stream));
   }
-  const long long stride = (long long)m->R * e->ni;
-  const size_t slot = (size_t)(m->k % m->R) * e->ni;
-  int rc = launch_march(e, m->nprob, m->X + slot, stride, m->Y + slot, stride, m->freeze ? m->done : nullptr, st);
+  const long long stride = (long long)m->R * m->n;
+  const size_t slot = (size_t)(m->k % m->R) * m->n;
+  int rc = e->diblock_state ? launch_residual_ab(e, m->nprob, m->X + slot, stride, m->Y + slot, stride, m->freeze ? m->done : nullptr, st)
+                            : launch_march(e, m->nprob, m->X + slot, stride, m->Y + slot, stride, m->freeze ? m->done : nullptr, st);
   if (rc) return rc;
   AndersonParams A;
-  A.n = e->ni; A.nprob = m->nprob; A.R = m->R; A.nm = m->nm; A.k = m->k; A.Final = m->Final;
+  A.n = m->n; A.nprob = m->nprob; A.R = m->R; A.nm = m->nm; A.k = m->k; A.Final = m->Final;
   A.tol = m->tol; A.lmd = m->lmd; A.freeze = m->freeze;
   A.adm = m->adm;
   A.relax = m->k == 0 ? 0.05 : 1.0 - std::pow(0.95, m->k + 1);   // adm.c:140 (its = 1), adm.c:151 (its = k+1)
@@ -363,7 +366,7 @@ int scftb_mixer_status(scftb_mixer *m, void *stream, int *done, int *iters, doub
 int scftb_mixer_get_x(scftb_mixer *m, void *stream, double *x) {
   if (!m || !x) return fail(SCFTB_ERR_ARG, "mixer: null argument");
   scftb_engine *e = m->e;
-  const size_t n = e->ni;
+  const size_t n = m->n;
   CK(cudaSetDevice(e->cfg.device));
   CK(cudaStreamSynchronize((cudaStream_t)stream));
   std::vector<int> done(m->nprob);
@@ -378,7 +381,7 @@ int scftb_mixer_get_x(scftb_mixer *m, void *stream, double *x) {
 int scftb_mixer_get_y(scftb_mixer *m, void *stream, int k, double *y) {
   if (!m || !y) return fail(SCFTB_ERR_ARG, "mixer: null argument");
   if (k < 0 || k >= m->k || k < m->k - m->R) return fail(SCFTB_ERR_STATE, "mixer: residual of that iteration is not in the ring");
-  const size_t n = m->e->ni;
+  const size_t n = m->n;
   CK(cudaSetDevice(m->e->cfg.device));
   CK(cudaStreamSynchronize((cudaStream_t)stream));
   CK(cudaMemcpy2D(y, sizeof(double) * n, m->Y + (size_t)(k % m->R) * n, sizeof(double) * m->R * n, sizeof(double) * n,

@@ -249,6 +249,11 @@ class Engine:
     # ---- two-species (AB diblock) extension: q and q+ as separate sweeps
     def set_diblock(self, fA, chiN, p=-1):
         _chk(lib().scftb_set_diblock(self._h, p, fA, chiN))
+        self.two_species = True
+
+    def unknowns(self):
+        """unknowns per problem: N-2, or 2(N-2) = (eta_A, eta_B) after set_diblock"""
+        return 2 * self.ni if getattr(self, "two_species", False) else self.ni
 
     def residual_ab(self, w):
         """w [2*ni] or [nprob, 2*ni] = (eta_A, eta_B) on the interior nodes -> residual of the same shape:
@@ -345,13 +350,13 @@ class AndersonBatch:
         return done, iters, err
 
     def x(self, stream_ptr=0):
-        out = np.zeros((self.nprob, self.eng.ni))
+        out = np.zeros((self.nprob, self.eng.unknowns()))
         _chk(lib().scftb_mixer_get_x(self._h, C.c_void_p(stream_ptr), _p(out)))
         return out
 
     def y(self, stream_ptr, k):
         """residuals F(X_k) of iteration k"""
-        out = np.zeros((self.nprob, self.eng.ni))
+        out = np.zeros((self.nprob, self.eng.unknowns()))
         _chk(lib().scftb_mixer_get_y(self._h, C.c_void_p(stream_ptr), k, _p(out)))
         return out
 

@@ -174,3 +174,38 @@ def test_argument_errors(sb):
     with pytest.raises(sb.ScftError):
         eng.set_diblock(0.5, 1.0)                       # IRK4: implicit-Euler schemes only
     eng.close()
+
+
+def test_device_mixers_on_two_species_engine_equal_host_flow_bitwise(sb, fixtures):
+    """adm_chen and adm, device-resident, on the (eta_A, eta_B) vector of a diblock engine: the same iterates, bit for bit,
+    as the reference-shaped host flows driven by scftb_callback_ab_c0 / its fixed-point image"""
+    N, n, jf = 33, 128, 32
+    ni = N - 2
+    em = fixtures["n33_eta"][1:-1]
+    x0 = np.concatenate([em, 0.8 * em])
+    L = sb.lib()
+    eng = sb.Engine(N, nsteps=n, scheme=0, max_batch=2)
+    eng.set_diblock(jf / n, 3.0)
+    eng.bind_global()
+    for (tol, mi, lmd, nn) in [(1e-30, 6, 0.9, 3), (1e-30, 40, 0.99, 2), (1e-30, 45, 0.9, 15)]:
+        xh = x0.copy()
+        rc_h = L.scftb_adm_chen(L.scftb_callback_ab_c0, xh.ctypes.data_as(_dp), tol, mi, 2 * ni, lmd, nn, 0)
+        rc_d, xd, iters, err = eng.adm_chen_batch(np.stack([x0, 1.01 * x0]), tol, mi, lmd, nn)
+        assert (rc_h == 0) == (rc_d == 0)
+        assert xd.shape == (2, 2 * ni) and np.array_equal(xh, xd[0]), np.abs(xh - xd[0]).max()
+    # adm: x -> x + F(x) on the two-species residual
+    FUNC = C.CFUNCTYPE(None, C.c_int, _dp, _dp)
+
+    @FUNC
+    def fixed_point(nn_, pin, pout):
+        L.scftb_callback_ab_c0(nn_, pin, pout)
+        for i in range(nn_):
+            pout[i] += pin[i]
+
+    for maxits in (1, 3, 14):
+        xh = x0.copy()
+        chk = C.c_int(1)
+        L.scftb_adm(fixed_point, xh.ctypes.data_as(_dp), 2 * ni, C.byref(chk), maxits)
+        rc_d, xd, iters, err = eng.adm_batch(x0[None, :], maxits)
+        assert np.array_equal(xh, xd[0]), (maxits, np.abs(xh - xd[0]).max())
+    eng.close()
