@@ -30,7 +30,6 @@
 namespace scftb {
 
 constexpr int PM_T = 256;
-constexpr int PM_EPT = 16;       // nodes per thread: n <= 4096 (the march kernels' own limit)
 constexpr int PM_NN_MAX = 16;
 constexpr int PM_NW = PM_T / 32;
 
@@ -53,13 +52,17 @@ __device__ __forceinline__ double pm_wsum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(PM_T) pmix_kernel(PMixParams A) {
+constexpr int PM_TILE = 128;    // nodes per shared-memory tile of the Gram-matrix pass
+
+__global__ void __launch_bounds__(PM_T, 4) pmix_kernel(PMixParams A) {
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (A.done[p]) return;
   const int n = A.n, R = A.R, k = A.k;
   __shared__ double s_red[PM_NW];
   __shared__ int s_bad[PM_NW];
   __shared__ double s_U[PM_NN_MAX * PM_NN_MAX], s_V[PM_NN_MAX];
+  __shared__ double s_D[PM_NN_MAX + 1][PM_TILE + 1];   // rows j < m: G_k - G_{k-j-1}; row m: G_k  (one tile of nodes)
+  __shared__ int s_ipiv[PM_NN_MAX];
   __shared__ double s_scalar[3];
   __shared__ int s_m, s_kr;
   if (tid == 0) { s_scalar[1] = A.best[p]; s_scalar[2] = A.beta[p]; s_kr = A.k_restart[p]; }   // read once, before anyone writes them
@@ -107,15 +110,11 @@ __global__ void __launch_bounds__(PM_T) pmix_kernel(PMixParams A) {
   }
 
   // ---- G_k = -(F + Psi^-1 (1/2)(-Lap_h) Psi^-1 F), F = phi0 - phi
-  const double *ph = A.phi + (size_t)p * A.N;
-  const double *xn = A.xnode ? A.xnode + (size_t)p * A.N : nullptr;
-  const double h = A.L[p] / (A.N - 1), ih2 = 1.0 / (h * h);
-  double gk[PM_EPT], xk[PM_EPT];
-#pragma unroll
-  for (int q = 0; q < PM_EPT; q++) {
-    const int i = tid + q * PM_T;
-    gk[q] = 0.0; xk[q] = 0.0;
-    if (i < n) {
+  {
+    const double *ph = A.phi + (size_t)p * A.N;
+    const double *xn = A.xnode ? A.xnode + (size_t)p * A.N : nullptr;
+    const double h = A.L[p] / (A.N - 1), ih2 = 1.0 / (h * h);
+    for (int i = tid; i < n; i += PM_T) {
       const double psi = sqrt(fmax(ph[i + 1], 1e-12));
       const double f = A.sign * Fp[i], u = f / psi;
       const double um = i > 0 ? A.sign * Fp[i - 1] / sqrt(fmax(ph[i], 1e-12)) : 0.0;
@@ -126,101 +125,117 @@ __global__ void __launch_bounds__(PM_T) pmix_kernel(PMixParams A) {
         const double hl = xn[i + 1] - xn[i], hr = xn[i + 2] - xn[i + 1];
         lap = -2.0 / (hl + hr) * ((up - u) / hr - (u - um) / hl);
       }
-      gk[q] = -(f + 0.5 * lap / psi);
-      xk[q] = Xk[i];
-      Gk[i] = gk[q];
+      Gk[i] = -(f + 0.5 * lap / psi);
     }
   }
   __syncthreads();   // G_k visible to the whole CTA
 
-  // ---- Gram matrix of the residual differences and right-hand side (ADM_chen_C.c:89-101), a warp per entry
+  // ---- Gram matrix of the residual differences and right-hand side (ADM_chen_C.c:89-101).  The differences of one tile
+  // of nodes are staged in shared memory (every ring vector is read from L2 exactly once); entry (i <= j) of U or V_i is
+  // owned by SP consecutive lanes that split the tile, SP = 4, 2 or 1 so that E * SP <= 256
   int m = min(A.nm, k - s_kr);
   if (m > 0) {
     const int E1 = m * (m + 1) / 2, E = E1 + m;
-    for (int eidx = wid; eidx < E; eidx += PM_NW) {
-      int i, j;
-      if (eidx < E1) { i = 0; int rem = eidx; while (rem >= m - i) { rem -= m - i; i++; } j = i + rem; }
-      else { i = eidx - E1; j = -1; }
-      const double *Gi = Gp + (size_t)((k - i - 1) % R) * n;
-      const double *Gj = j >= 0 ? Gp + (size_t)((k - j - 1) % R) * n : nullptr;
-      double s = 0.0;
-      for (int t = lane; t < n; t += 32) {
-        const double g = Gk[t], di = g - Gi[t];
-        s = fma(di, Gj ? g - Gj[t] : g, s);
-      }
-      s = pm_wsum(s);
-      if (lane == 0) {
-        if (j >= 0) { s_U[i * m + j] = s; s_U[j * m + i] = s; } else s_V[i] = s;
-      }
+    const int SP = (4 * E <= PM_T) ? 4 : ((2 * E <= PM_T) ? 2 : 1);
+    const int ent = tid / SP, part = tid - ent * SP;
+    int ri = 0, rj = 0;
+    const bool active = ent < E;
+    if (active) {
+      if (ent < E1) { int i = 0, rem = ent; while (rem >= m - i) { rem -= m - i; i++; } ri = i; rj = i + rem; }
+      else { ri = ent - E1; rj = m; }   // V_i = <D_i, G_k>: row m of the tile is G_k
     }
-    __syncthreads();
-    if (tid == 0) {   // full-pivoting Gauss-Jordan on the m x m system (gaussj.c:19-73), m <= 16
-      int ipiv[PM_NN_MAX];
-      for (int i = 0; i < m; i++) ipiv[i] = 0;
-      bool sing = false;
-      for (int it = 0; it < m && !sing; it++) {
-        double big = -1.0; int irow = -1, icol = -1;
-        for (int j = 0; j < m; j++)
-          if (ipiv[j] != 1)
-            for (int c = 0; c < m; c++)
-              if (ipiv[c] == 0) { const double v = fabs(s_U[j * m + c]); if (v >= big) { big = v; irow = j; icol = c; } }
-        if (irow < 0 || !(big > 0.0) || !isfinite(big)) { sing = true; break; }
-        ipiv[icol]++;
-        if (irow != icol) {
-          for (int l = 0; l < m; l++) { const double tmp = s_U[irow * m + l]; s_U[irow * m + l] = s_U[icol * m + l]; s_U[icol * m + l] = tmp; }
-          const double tmp = s_V[irow]; s_V[irow] = s_V[icol]; s_V[icol] = tmp;
+    double acc = 0.0;
+    for (int t0 = 0; t0 < n; t0 += PM_TILE) {
+      const int len = min(PM_TILE, n - t0);
+      for (int idx = tid; idx < (m + 1) * PM_TILE; idx += PM_T) {
+        const int j = idx / PM_TILE, tt = idx - j * PM_TILE;
+        if (tt < len) {
+          const double g = Gk[t0 + tt];
+          s_D[j][tt] = (j < m) ? g - Gp[(size_t)((k - j - 1) % R) * n + t0 + tt] : g;
         }
-        const double pivinv = 1.0 / s_U[icol * m + icol];
-        s_U[icol * m + icol] = 1.0;
-        for (int l = 0; l < m; l++) s_U[icol * m + l] *= pivinv;
-        s_V[icol] *= pivinv;
-        for (int ll = 0; ll < m; ll++)
-          if (ll != icol) {
-            const double dum = s_U[ll * m + icol];
-            s_U[ll * m + icol] = 0.0;
-            for (int l = 0; l < m; l++) s_U[ll * m + l] -= s_U[icol * m + l] * dum;
-            s_V[ll] -= s_V[icol] * dum;
-          }
       }
-      for (int i = 0; i < m && !sing; i++) if (!isfinite(s_V[i])) sing = true;
-      if (sing) { A.k_restart[p] = k; s_m = 0; } else s_m = m;   // restart with an empty history (ADM_chen_C.c:106-112)
+      __syncthreads();
+      if (active) {
+        const double *di = s_D[ri], *dj = s_D[rj];
+        for (int tt = part; tt < len; tt += SP) acc = fma(di[tt], dj[tt], acc);
+      }
+      __syncthreads();
+    }
+    if (SP >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (SP >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (active && part == 0) {
+      if (rj == m) s_V[ri] = acc; else { s_U[ri * m + rj] = acc; s_U[rj * m + ri] = acc; }
+    }
+    if (tid < m) s_ipiv[tid] = 0;
+    __syncthreads();
+    // full-pivoting Gauss-Jordan on the m x m system (gaussj.c:19-73; pivot = LAST maximum in row-major order) by warp 0:
+    // lane l owns row l
+    if (wid == 0) {
+      bool sing = false;
+      for (int it = 0; it < m; it++) {
+        double big = -1.0; int bcol = -1;
+        if (lane < m && s_ipiv[lane] != 1)
+          for (int c = 0; c < m; c++)
+            if (s_ipiv[c] == 0) { const double v = fabs(s_U[lane * m + c]); if (v >= big) { big = v; bcol = c; } }
+        int brow = (bcol >= 0) ? lane : -1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, big, d);
+          const int orow = __shfl_xor_sync(0xffffffffu, brow, d), ocol = __shfl_xor_sync(0xffffffffu, bcol, d);
+          if (orow >= 0 && (brow < 0 || ob > big || (ob == big && orow > brow))) { big = ob; brow = orow; bcol = ocol; }
+        }
+        if (brow < 0 || !(big > 0.0) || !isfinite(big)) { sing = true; break; }
+        const int irow = brow, icol = bcol;
+        if (lane == 0) s_ipiv[icol]++;
+        if (irow != icol) {
+          if (lane < m) { const double tmp = s_U[irow * m + lane]; s_U[irow * m + lane] = s_U[icol * m + lane]; s_U[icol * m + lane] = tmp; }
+          if (lane == 0) { const double tmp = s_V[irow]; s_V[irow] = s_V[icol]; s_V[icol] = tmp; }
+        }
+        __syncwarp();
+        const double pivinv = 1.0 / s_U[icol * m + icol];
+        __syncwarp();
+        if (lane < m) s_U[icol * m + lane] = (lane == icol) ? pivinv : s_U[icol * m + lane] * pivinv;
+        if (lane == 0) s_V[icol] *= pivinv;
+        __syncwarp();
+        if (lane < m && lane != icol) {
+          const double dum = s_U[lane * m + icol];
+          s_U[lane * m + icol] = 0.0;
+          for (int c = 0; c < m; c++) s_U[lane * m + c] -= s_U[icol * m + c] * dum;
+          s_V[lane] -= s_V[icol] * dum;
+        }
+        __syncwarp();
+      }
+      if (!sing && lane < m && !isfinite(s_V[lane])) sing = true;
+      sing = __any_sync(0xffffffffu, sing);
+      if (lane == 0) { if (sing) { A.k_restart[p] = k; s_m = 0; } else s_m = m; }   // restart with an empty history (ADM_chen_C.c:106-112)
     }
     __syncthreads();
     m = s_m;
   }
 
   // ---- X_{k+1} = X_k + sum_j V_j (X_{k-j-1} - X_k) + beta (G_k + sum_j V_j (G_{k-j-1} - G_k))   (ADM_chen_C.c:114-123)
-  double dx[PM_EPT], smax = 0.0;
-#pragma unroll
-  for (int q = 0; q < PM_EPT; q++) {
-    const int i = tid + q * PM_T;
-    dx[q] = 0.0;
-    if (i < n) {
-      double cx = 0.0, cd = 0.0;
-      for (int j = 0; j < m; j++) {
-        const size_t s = (size_t)((k - j - 1) % R) * n + i;
-        cx = fma(s_V[j], Xp[s] - xk[q], cx);
-        cd = fma(s_V[j], Gp[s] - gk[q], cd);
-      }
-      dx[q] = cx + beta * (gk[q] + cd);
-      smax = fmax(smax, fabs(dx[q]));
+  double smax = 0.0;
+  for (int i = tid; i < n; i += PM_T) {
+    const double xk = Xk[i], gk = Gk[i];
+    double cx = 0.0, cd = 0.0;
+    for (int j = 0; j < m; j++) {
+      const size_t s = (size_t)((k - j - 1) % R) * n + i;
+      cx = fma(s_V[j], Xp[s] - xk, cx);
+      cd = fma(s_V[j], Gp[s] - gk, cd);
     }
+    const double dx = cx + beta * (gk + cd);
+    Xn[i] = xk + dx;
+    smax = fmax(smax, fabs(dx));
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, d));
   if (lane == 0) s_red[wid] = smax;
   __syncthreads();
-  if (tid == 0) {
-    double s = 0.0;
-    for (int w = 0; w < PM_NW; w++) s = fmax(s, s_red[w]);
-    s_scalar[0] = (e > 1e-2 && s > A.cap) ? A.cap / s : 1.0;
-  }
-  __syncthreads();
-  const double scale = s_scalar[0];
-#pragma unroll
-  for (int q = 0; q < PM_EPT; q++) {
-    const int i = tid + q * PM_T;
-    if (i < n) Xn[i] = xk[q] + scale * dx[q];
+  double s = 0.0;
+  for (int w = 0; w < PM_NW; w++) s = fmax(s, s_red[w]);
+  if (e > 1e-2 && s > A.cap) {   // far from the solution: scale the step to max|dx| = cap (each thread rescales its own nodes)
+    const double scale = A.cap / s;
+    for (int i = tid; i < n; i += PM_T) { const double xk = Xk[i]; Xn[i] = xk + scale * (Xn[i] - xk); }
   }
 }
 
@@ -330,7 +345,6 @@ int scftb_pmixer_destroy(scftb_pmixer *m) {
 int scftb_pmixer_create(scftb_engine *e, int nprob, double tol, int nn, double cap, scftb_pmixer **out) {
   if (!e || !out || nprob < 1 || nprob > e->cfg.max_batch) return fail(SCFTB_ERR_ARG, "pmixer: bad argument");
   if (nn < 0 || nn > PM_NN_MAX) return fail(SCFTB_ERR_ARG, "pmixer: mixing window nn must be in [0, 16]");
-  if (e->ni > PM_T * PM_EPT) return fail(SCFTB_ERR_ARG, "pmixer: more than 4096 unknowns");
   if (e->diblock_state) return fail(SCFTB_ERR_STATE, "pmixer: one-species engines only");
   scftb_pmixer *m = new scftb_pmixer();
   m->e = e; m->nprob = nprob; m->nn = nn; m->nm = std::min(nn, e->ni); m->R = m->nm + 2; m->k = 0;

@@ -128,3 +128,21 @@ def test_sweep_solver_continuation_to_257(fixtures):
         assert abs(F - rows[p, 4]) <= 1e-9 * abs(F)
     r2 = sweep.converge_block_batched(256, 258, eta33, levels=4)     # same cells as problems 0, 1; other seeds
     assert np.max(np.abs(r2["rows"][:, 4] - rows[:2, 4])) <= 1e-9 * np.abs(rows[:2, 4]).max()
+
+
+def test_sweep_solver_to_m1024(fixtures):
+    """BASELINE.json configs[2] at full size for a block of the sweep: 48 problems (three (tau, L) rows of the grid) through all
+    six levels to N = 1025, n = 2048; every problem converges in <= 12 evaluations on the target mesh; two fields are
+    re-evaluated by the CPU oracle"""
+    from scft_b200 import sweep
+    eta33 = fixtures["n33_eta"][1:-1]
+    r = sweep.converge_block_batched(100, 148, eta33, levels=6, want_fields=True)
+    rows = r["rows"]
+    assert np.all(rows[:, 0] == 0) and np.all(rows[:, 1] < 1e-9) and np.all(rows[:, 6] == 1025), rows[rows[:, 0] != 0]
+    assert rows[:, 5].max() <= 12
+    for i in (0, 47):
+        tau, L, _ = sweep.sweep_params(100 + i)
+        res, Q, F = _oracle_check(1025, tau, L, r["eta"][i])
+        assert res < 2e-9
+        assert abs(Q - rows[i, 3]) <= 1e-10 * abs(Q)
+        assert abs(F - rows[i, 4]) <= 1e-9 * abs(F)
