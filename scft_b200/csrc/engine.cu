@@ -15,6 +15,7 @@
 #include "march1d.cuh"
 #include "march_irk4.cuh"
 #include "march1d_tmem.cuh"
+#include "march_irk4_tm.cuh"
 
 namespace scftb {
 
@@ -175,7 +176,7 @@ static march_fn pick4(bool uni) {
   return uni ? (march_fn)march_irk4_kernel<C, T, true> : (march_fn)march_irk4_kernel<C, T, false>;
 }
 
-int choose_kernel_irk4(int ni, bool uni, KernelChoice &kc) {
+int choose_kernel_irk4(int ni, bool uni, KernelChoice &kc, int max_batch) {
   int C = 1;
   while (C < 8 && (ni + C - 1) / C > 256) C *= 2;
   int need = (ni + C - 1) / C;
@@ -191,11 +192,20 @@ int choose_kernel_irk4(int ni, bool uni, KernelChoice &kc) {
   if (C == 8 && T == 256) kc.fn = pick4<8, 256>(uni);
   if (!kc.fn) return 1;
   kc.C = C; kc.T = T; kc.dyn_smem = 0; kc.max_occ = 0;
+  // 513..1024 unknowns on a uniform mesh: complex coefficients in tensor memory, <= 128 registers, two CTAs (16 warps) per SM
+  // — a throughput kernel (+18 % on sweeps); one CTA alone is 17 % SLOWER than the register-resident kernel (2253 vs 1925
+  // cycles per step: the tcgen05.ld waits sit on its critical path), so engines that can never fill more than one CTA per
+  // SM (max_batch <= 148: single problems, small Jacobian batches) keep the register-resident kernel
+  const char *no_tm = getenv("SCFTB_NO_TMEM");
+  if (C == 4 && T == 256 && uni && max_batch > 148 && !(no_tm && atoi(no_tm))) {
+    kc.fn = (march_fn)march_irk4_tm_kernel;
+    kc.max_occ = 2;
+  }
   return 0;
 }
 
-static int choose_any(int scheme, int ni, bool uni, KernelChoice &kc, int nsteps) {
-  return scheme == SCFTB_IRK4_CONSISTENT ? choose_kernel_irk4(ni, uni, kc) : choose_kernel(ni, uni, kc, (nsteps & 1) != 0);
+static int choose_any(int scheme, int ni, bool uni, KernelChoice &kc, int nsteps, int max_batch) {
+  return scheme == SCFTB_IRK4_CONSISTENT ? choose_kernel_irk4(ni, uni, kc, max_batch) : choose_kernel(ni, uni, kc, (nsteps & 1) != 0);
 }
 
 }  // namespace scftb
@@ -258,7 +268,7 @@ int scftb_create(const scftb_config *cfg, scftb_engine **out) {
   // sum_j w_j q_j q_{n-j} = sum_{j>n/2} 2 w_j q_j q_{n-j} + [n even] w_{n/2} q_{n/2}^2
   std::vector<double> wq(e->h_w);
   for (int j = 0; j <= n; j++) wq[j] = (2 * j > n) ? 2.0 * e->h_w[j] : ((2 * j == n) ? e->h_w[j] : 0.0);
-  if (choose_any(cfg->scheme, e->ni, true, e->kc, cfg->nsteps)) {
+  if (choose_any(cfg->scheme, e->ni, true, e->kc, cfg->nsteps, cfg->max_batch)) {
     delete e;
     return fail(SCFTB_ERR_ARG, cfg->scheme == SCFTB_IRK4_CONSISTENT
                                    ? "N too large for the register-resident IRK4 march (N <= 2050 in this build)"
@@ -339,8 +349,8 @@ int scftb_engine_max_batch(scftb_engine *e) { return e ? e->cfg.max_batch : 0; }
 
 int scftb_get_kernel_name(scftb_engine *e, char *buf, int len) {
   if (!e || !buf || len < 1) return fail(SCFTB_ERR_ARG, "null argument");
-  const bool tm = e->kc.fn == (march_fn)march_tm_kernel;
-  snprintf(buf, len, "%s<%d,%d,%s>%s", e->cfg.scheme == SCFTB_IRK4_CONSISTENT ? "march_irk4_kernel" : (tm ? "march_tm_kernel" : "march_ie_kernel"),
+  const bool tm = e->kc.fn == (march_fn)march_tm_kernel || e->kc.fn == (march_fn)march_irk4_tm_kernel;
+  snprintf(buf, len, "%s<%d,%d,%s>%s", e->cfg.scheme == SCFTB_IRK4_CONSISTENT ? (tm ? "march_irk4_tm_kernel" : "march_irk4_kernel") : (tm ? "march_tm_kernel" : "march_ie_kernel"),
            e->kc.C, e->kc.T, e->uniform ? "uniform" : "mesh", tm ? " (coefficients in tensor memory)" : "");
   return SCFTB_OK;
 }
@@ -380,7 +390,7 @@ int scftb_set_problem(scftb_engine *e, int p, double tau, double L, const double
     for (int q = 0; q < B; q++)
       for (int i = 0; i < N; i++) e->h_x[(size_t)q * N + i] = e->h_L[q] * i / (N - 1);
     e->uniform = false;
-    if (choose_any(e->cfg.scheme, e->ni, false, e->kc, e->cfg.nsteps)) return fail(SCFTB_ERR_ARG, "N too large");
+    if (choose_any(e->cfg.scheme, e->ni, false, e->kc, e->cfg.nsteps, e->cfg.max_batch)) return fail(SCFTB_ERR_ARG, "N too large");
   }
   std::vector<double> xs(N);
   for (int q = (p < 0 ? 0 : p); q < (p < 0 ? B : p + 1); q++) {

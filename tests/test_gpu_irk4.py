@@ -100,3 +100,32 @@ def test_broydn_reproduces_reference_convergence_from_fixture(sb, oracle, fixtur
     eng.residual(x)
     assert eng.free_energy() == pytest.approx(float(fixtures["n33_F"]), abs=2e-12)
     eng.close()
+
+
+@pytest.mark.parametrize("nsteps,store", [(2048, False), (64, False), (64, True), (33, False)])
+def test_irk4_tensor_memory_kernel_sweep(sb, oracle, fixtures, nsteps, store):
+    """march_irk4_tm_kernel (complex coefficients in tensor memory; selected for 513..1024 unknowns, uniform mesh,
+    max_batch > 148): 300 sweep problems at N = 1025 — more than the 296 resident CTA slots, so slots are reused — with
+    per-problem (tau, L); problems around the wave boundaries against the oracle's block-LU march, lean and full history,
+    even and odd step counts"""
+    from scft_b200 import sweep
+    N, P = 1025, 300
+    taus, Ls, eta = sweep.make_sweep(0, P, fixtures["res1024_eta"][1:-1])
+    quad = sb.QUAD_ROMBERG if nsteps in (2048, 64) else sb.QUAD_TRAPEZOID
+    eng = sb.Engine(N, nsteps=nsteps, scheme=sb.IRK4_CONSISTENT, max_batch=P, store_history=store, quadrature=quad)
+    assert "march_irk4_tm_kernel" in eng.kernel_name() and eng.slots() == 296
+    for p in range(P):
+        eng.set_problem(p, taus[p], Ls[p])
+    out = eng.residual(eta)
+    for p in ((0, 147, 148, 295, 296, 299) if nsteps != 2048 else (0, 296, 299)):
+        x = oracle.mesh_uniform(N, Ls[p])
+        ref = oracle.residual(oracle.eta_full(x, eta[p]), oracle.f0_given(x, taus[p]), scheme=oracle.IRK4_CONSISTENT, nsteps=nsteps,
+                              L=Ls[p], quadrature=oracle.QUAD_ROMBERG if quad == sb.QUAD_ROMBERG else oracle.QUAD_TRAPEZOID,
+                              want_hist=store)
+        scale = np.abs(ref["phi"]).max()
+        assert np.abs(eng.phi(p) - ref["phi"]).max() < REL * scale
+        assert abs(eng.Q(p) - ref["Q"]) < REL * abs(ref["Q"])
+        assert np.abs(out[p] - ref["out"]).max() < REL * scale
+        if store and p in (0, 299):
+            assert np.abs(eng.q_history(p) - ref["hist"]).max() < 1e-11
+    eng.close()
