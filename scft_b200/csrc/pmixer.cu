@@ -608,15 +608,18 @@ int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double
     pcell[p] = it->second;
   }
   std::vector<double> cw((size_t)cells.size() * Nt), cf0(cells.size());
+  // started when the LAST level begins: its iterations are long kernels, so the host threads do not disturb the polling
+  // loop the way they would on the latency-bound coarse levels, and they finish well inside that level's GPU time
   std::vector<std::thread> workers;
-  {
-    const int nthr = (int)std::max(1u, std::min(16u, std::min((unsigned)cells.size(), std::thread::hardware_concurrency())));
+  auto start_workers = [&]() {
+    const unsigned hc = std::max(2u, std::thread::hardware_concurrency());
+    const int nthr = (int)std::max(1u, std::min(std::min(16u, hc - 1), (unsigned)cells.size()));
     for (int t = 0; t < nthr; t++)
       workers.emplace_back([&, t, nthr]() {
         for (size_t c = t; c < cells.size(); c += nthr)
           free_energy_weights(Nt, nullptr, cells[c].first, cells[c].second, &cw[c * Nt], &cf0[c]);
       });
-  }
+  };
   auto join = [&]() { for (auto &w : workers) if (w.joinable()) w.join(); };
   int rc = SCFTB_OK;
   double *cur = s->d_a, *nxt = s->d_b;
@@ -638,6 +641,7 @@ int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double
       ce = cudaMemcpy(m->done, dead.data(), sizeof(int) * nprob, cudaMemcpyHostToDevice);
       if (ce != cudaSuccess) { rc = fail(SCFTB_ERR_CUDA, cudaGetErrorString(ce)); break; }
     }
+    if (lvl == levels - 1) start_workers();
     rc = pmixer_run(m, s->cfg.maxit, done, nullptr);
     if (!rc) rc = scftb_pmixer_status(m, e->stream, done.data(), iters.data(), err.data());
     if (rc) break;
