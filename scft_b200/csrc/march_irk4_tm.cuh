@@ -6,7 +6,7 @@
 // SM) and runs at 34 % of the fp64 pipe, latency-bound.  Here each thread keeps 56 doubles in its TMEM lane (warps 0-3 in
 // columns [0,112), warps 4-7 — which map onto the same 128 lanes — in [112,224)) and streams them back with tcgen05.ld one
 // phase ahead of use; the eight per-warp level-3 constants come from shared memory.  <= 128 registers, 2 CTAs = 16 warps per
-// SM (2 x 256 columns = the whole tensor memory).  Measured: 1.55e11 -> 1.79e11 DOF-steps/s on the 4096-problem sweep; with 16
+// SM (2 x 256 columns = the whole tensor memory).  Measured: 1.52e11 -> 1.89e11 DOF-steps/s on the 4096-problem sweep; with 16
 // warps the kernel is ISSUE-bound (407 SASS instructions per warp-step for 128 nodes, 74 of them 32-bit shuffles of the
 // complex cyclic reduction; ncu: issue slots 48 %, fp64 pipe 41 %), so the next lever is C = 8 nodes per thread, not
 // occupancy.  A variant that keeps the chunk-sweep coefficients in registers and loads everything else at the top of the
@@ -259,13 +259,18 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
     tm_pin(rA);
 
     // ---------------------------------------------------------------- the contour march
-    for (int j = 1; j <= n; j++) {
-      const bool pairing = (2 * j > n);
+    // PH = 0: 2j < n (store the slice), 1: 2j = n (pairs with itself), 2: 2j > n (pairs with slice n-j); one instantiation
+    // per phase keeps the selects and branches of the quadrature out of the step
+    const bool l0 = (lane == 0), l30 = (lane == 30), l31 = (lane == 31);
+    double *hw = hb;                              // write cursor (slice j)
+    const double *hr = hb + (size_t)n * SL;       // read cursor (slice n-j)
+    auto step = [&](auto ph, const int j) {
+      constexpr int PH = decltype(ph)::value;
+      hw += SL; hr -= SL;
       double2 qo01 = make_double2(0.0, 0.0), qo23 = make_double2(0.0, 0.0);
-      if (pairing) {
-        const double *hs = hb + (size_t)(n - j) * SL;
-        qo01 = *reinterpret_cast<const double2 *>(hs);
-        qo23 = *reinterpret_cast<const double2 *>(hs + 2 * T);
+      if (PH == 2) {
+        qo01 = *reinterpret_cast<const double2 *>(hr);
+        qo23 = *reinterpret_cast<const double2 *>(hr + 2 * T);
       }
       uint32_t rB1[8];
       tm_ld8(tb + TM4_B1, rB1);
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
         cx zfn = shfl_dn_c(z[0], 1);
         r = nfma(su, zfn, r);
       }
-      if (lane == 31) r = mk(0.0);
+      if (l31) r = mk(0.0);
       // ---- level 2 (block B2): five cyclic-reduction stages
 #define IRK4_CR_STAGE(S, PG)                                                    \
       {                                                                             \
@@ -313,9 +318,9 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
       tm_pin(rC); tm_pin(rA);
       const cx Z = r * tm_getc(rC, 0);
       double *pb = s_pub[j & 1][wid];
-      if (lane == 0) { pb[0] = q[0]; pb[2] = z[0].re; pb[3] = z[0].im; pb[4] = Z.re; pb[5] = Z.im; }
-      if (lane == 30) { pb[6] = Z.re; pb[7] = Z.im; }
-      if (lane == 31) { pb[8] = rsep.re; pb[9] = rsep.im; }
+      if (l0) { pb[0] = q[0]; pb[2] = z[0].re; pb[3] = z[0].im; pb[4] = Z.re; pb[5] = Z.im; }
+      if (l30) { pb[6] = Z.re; pb[7] = Z.im; }
+      if (l31) { pb[8] = rsep.re; pb[9] = rsep.im; }
       __syncthreads();
       cx Wm, Ww;
       {
@@ -335,9 +340,9 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
           Wm.re += __shfl_xor_sync(0xffffffffu, Wm.re, d); Wm.im += __shfl_xor_sync(0xffffffffu, Wm.im, d);
         }
       }
-      const cx Y = (lane == 31) ? Ww : nfma(tm_getc(rC, 1), Wm, nfma(tm_getc(rC, 2), Ww, Z));   // solution at the own separator
+      const cx Y = l31 ? Ww : nfma(tm_getc(rC, 1), Wm, nfma(tm_getc(rC, 2), Ww, Z));   // solution at the own separator
       cx YL = shfl_up_c(Y, 1);
-      if (lane == 0) YL = Wm;                                                                  // previous warp's separator
+      if (l0) YL = Wm;                                                                 // previous warp's separator
       // q+ = q - 2 Re[alpha y]
       {
         cx y0 = nfma(tm_getc(rC, 3), YL, nfma(tm_getc(rC, 6), Y, z[0]));
@@ -350,16 +355,21 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
       q[C - 1] = fma(-a_re, Y.re, fma(-a_im, Y.im, q[C - 1]));
       XL = fma(-a_re, YL.re, fma(-a_im, YL.im, XL));
       qn = shfl_dn_d(q[0], 1);
-      if (lane == 31) qn = 0.0;
-      if (full || 2 * j < n) store_slice(hb + (size_t)j * SL);
-      if (2 * j >= n) {
+      if (l31) qn = 0.0;
+      if (PH == 0 || full) store_slice(hw);
+      if (PH >= 1) {
         const double wj = __ldg(P.w + j);
-        phi[0] = fma(wj * q[0], pairing ? qo01.x : q[0], phi[0]);
-        phi[1] = fma(wj * q[1], pairing ? qo01.y : q[1], phi[1]);
-        phi[2] = fma(wj * q[2], pairing ? qo23.x : q[2], phi[2]);
-        phi[3] = fma(wj * q[3], pairing ? qo23.y : q[3], phi[3]);
+        phi[0] = fma(wj * q[0], PH == 2 ? qo01.x : q[0], phi[0]);
+        phi[1] = fma(wj * q[1], PH == 2 ? qo01.y : q[1], phi[1]);
+        phi[2] = fma(wj * q[2], PH == 2 ? qo23.x : q[2], phi[2]);
+        phi[3] = fma(wj * q[3], PH == 2 ? qo23.y : q[3], phi[3]);
       }
-    }
+    };
+    int j = 1;
+    // (two steps per loop trip, as in march_tm_kernel, spill 780 B here and are 1.5 % slower)
+    for (; 2 * j < n; j++) step(std::integral_constant<int, 0>{}, j);
+    if (2 * j == n) { step(std::integral_constant<int, 1>{}, j); j++; }
+    for (; j <= n; j++) step(std::integral_constant<int, 2>{}, j);
 
     // ---------------------------------------------------------------- residual, phi, Q
     double qsum = 0.0;

@@ -47,7 +47,8 @@ def test_csr_matrices_match_oracle(sb, nx, ny, nsteps):
     eng.close()
 
 
-@pytest.mark.parametrize("nx,ny,nsteps,kind", [(32, 4, 64, "yinv"), (32, 8, 64, "ymod"), (48, 12, 32, "rand"), (128, 16, 16, "rand")])
+@pytest.mark.parametrize("nx,ny,nsteps,kind", [(32, 4, 64, "yinv"), (32, 8, 64, "ymod"), (48, 12, 32, "rand"), (128, 16, 16, "rand"),
+                                               (128, 128, 16, "ymod")])   # y-modulated field on a 129^2 mesh
 def test_march_matches_oracle(sb, nx, ny, nsteps, kind):
     from oracle import oracle as O, oracle2d as O2
     rng = np.random.default_rng(ny)
