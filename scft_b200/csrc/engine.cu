@@ -192,13 +192,14 @@ int choose_kernel_irk4(int ni, bool uni, KernelChoice &kc, int max_batch) {
   if (C == 8 && T == 256) kc.fn = pick4<8, 256>(uni);
   if (!kc.fn) return 1;
   kc.C = C; kc.T = T; kc.dyn_smem = 0; kc.max_occ = 0;
-  // 513..1024 unknowns on a uniform mesh: complex coefficients in tensor memory, <= 128 registers, two CTAs (16 warps) per SM
-  // — a throughput kernel (+18 % on sweeps); one CTA alone is 17 % SLOWER than the register-resident kernel (2253 vs 1925
-  // cycles per step: the tcgen05.ld waits sit on its critical path), so engines that can never fill more than one CTA per
-  // SM (max_batch <= 148: single problems, small Jacobian batches) keep the register-resident kernel
+  // 513..1024 unknowns on a uniform mesh: complex coefficients in tensor memory (march_irk4_tm.cuh), two CTAs per SM — a
+  // throughput kernel (+76 % on sweeps); the tcgen05.ld waits sit on a lone CTA's critical path (the C = 4 version measured
+  // 2253 vs 1925 cycles per step), so engines that can never fill more than one CTA per SM (max_batch <= 148: single
+  // problems, small Jacobian batches) keep the register-resident kernel
   const char *no_tm = getenv("SCFTB_NO_TMEM");
   if (C == 4 && T == 256 && uni && max_batch > 148 && !(no_tm && atoi(no_tm))) {
     kc.fn = (march_fn)march_irk4_tm_kernel;
+    kc.C = 8; kc.T = 128;   // 8 nodes per thread: one separator per 8 nodes
     kc.max_occ = 2;
   }
   return 0;

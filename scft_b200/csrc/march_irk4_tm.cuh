@@ -1,30 +1,25 @@
 // march_irk4_tm.cuh — the IRK4 contour march (march_irk4.cuh: the reference's 2-stage Gauss-Legendre stepper as ONE complex
 // symmetric tridiagonal solve per step; scft.cc:671-693, drivescft.cc:130-146) for the benchmarked shape — uniform mesh,
-// 513..1024 unknowns, C = 4 nodes per thread, T = 256 threads — with its loop-invariant complex coefficients in TENSOR MEMORY.
+// 513..1024 unknowns — with its loop-invariant complex coefficients in TENSOR MEMORY.
 //
-// Same algorithm and arithmetic as march_irk4_kernel<4,256,true>.  That kernel needs 218 registers (one CTA of 8 warps per
-// SM) and runs at 34 % of the fp64 pipe, latency-bound.  Here each thread keeps 56 doubles in its TMEM lane (warps 0-3 in
-// columns [0,112), warps 4-7 — which map onto the same 128 lanes — in [112,224)) and streams them back with tcgen05.ld one
-// phase ahead of use; the eight per-warp level-3 constants come from shared memory.  <= 128 registers, 2 CTAs = 16 warps per
-// SM (2 x 256 columns = the whole tensor memory).  Measured: 1.52e11 -> 1.89e11 DOF-steps/s on the 4096-problem sweep; with 16
-// warps the kernel is ISSUE-bound (407 SASS instructions per warp-step for 128 nodes, 74 of them 32-bit shuffles of the
-// complex cyclic reduction; ncu: issue slots 48 %, fp64 pipe 41 %), so the next lever is C = 8 nodes per thread, not
-// occupancy.  A variant that keeps the chunk-sweep coefficients in registers and loads everything else at the top of the
-// step spills more and is 3 % slower.
-//
-// TMEM column map of a thread (a double is two 32-bit columns):
-//   block A  [  0, 32)  al1, al2, ca0, ca1, ca2, be0, be1, sl          chunk sweeps, separator row       (complex)
-//   block B1 [ 32, 40)  su (complex), A_off, -                         separator row
-//   block B2 [ 40, 80)  pa[0..4], pg[0..4]                             cyclic reduction                  (complex)
-//   block C  [ 80,112)  binv, GL, GR, gl0, gl1, gl2, gr0, gr1          back substitution                 (complex; gr2 stays in registers)
+// Same algorithm and arithmetic as march_irk4_kernel<4,256,true> (218 registers, one CTA of 8 warps per SM, 34 % of the fp64
+// pipe, latency-bound: 1.52e11 DOF-steps/s on the 4096-problem sweep).  Two tensor-memory versions were built:
+//   C = 4, T = 256, 56 doubles per thread in TMEM, 128 registers, 2 CTAs = 16 warps per SM: 1.89e11.  With 16 warps that kernel is
+//     ISSUE-bound (406 SASS instructions per warp-step of 128 nodes, 74 of them 32-bit shuffles of the complex cyclic
+//     reduction and butterfly; ncu: issue slots 49 %, fp64 pipe 42 %) — occupancy was not the lever, instructions per node are.
+//   C = 8, T = 128 (this file): one separator per 8 nodes halves the level-2/3 share; 97 doubles per thread in TMEM (196 of the
+//     256 allocated columns), up to 255 registers for the state and the blocks in flight, 2 CTAs = 8 warps per SM: **2.68e11**
+//     (+76 %, 33 % of the HBM roofline; the fp64 pipe caps this scheme near 50 %).
+// The eight per-warp level-3 constants come from a conflict-free shared-memory table; the step is instantiated per quadrature
+// phase (store / middle / pairing).  A throughput kernel: the tcgen05.ld waits lengthen a lone CTA's step, so engines with
+// max_batch <= 148 keep the register-resident kernel (engine.cu).
 #pragma once
 #include "march1d_tmem.cuh"
 #include "march_irk4.cuh"
 
 namespace scftb {
 
-constexpr int TM4_COLS = 256, TM4_PER = 112;
-constexpr int TM4_A = 0, TM4_B1 = 32, TM4_B2 = 40, TM4_C = 80;
+constexpr int TM4_COLS = 256;
 
 __device__ __forceinline__ void tm4_alloc(uint32_t *smem_dst) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(TM4_COLS) : "memory");
@@ -49,8 +44,39 @@ __device__ __forceinline__ void tm_putc(uint32_t (&r)[NR], int i, cx v) { tm_put
 
 constexpr int C3S = 10;  // doubles per row of the level-3 constant table: 80-byte rows are 16-byte aligned and the eight rows a warp reads fall into disjoint banks
 
-__global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
-  constexpr int C = 4, T = 256, CI = 3, NW = 8, SL = T * C;
+// TMEM column map of a thread (a double is two 32-bit columns, a complex number four):
+//   block A  [  0, 80)  al[1..6], ca[0..6], be[0..5], sl                        (complex)
+//   block B  [ 80,128)  su, A_off, -, pa[0..4], pg[0..4]                        (complex but A_off)
+//   block C  [128,196)  binv, GL, GR, gl[0..6], gr[0..6]                        (complex)
+constexpr int TM8_A = 0, TM8_B = 80, TM8_C = 128;
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tm_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// store / load NC complex numbers (4 columns each) at taddr, in pieces of 16 and 4 columns
+template <int NC>
+__device__ __forceinline__ void tm_store_cx(uint32_t taddr, const cx (&v)[NC]) {
+  static_assert(NC % 1 == 0, "");
+  int done = 0;
+#pragma unroll
+  for (; done + 4 <= NC; done += 4) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) tm_putc(w, i, v[done + i]);
+    tm_st16(taddr + 4 * done, w);
+  }
+#pragma unroll
+  for (; done < NC; done++) {
+    uint32_t w[4];
+    tm_put(w, 0, v[done].re); tm_put(w, 1, v[done].im);
+    tm_st4(taddr + 4 * done, w);
+  }
+}
+
+__global__ void __launch_bounds__(128, 2) march_irk4_tm_kernel(MarchParams P) {
+  constexpr int C = 8, T = 128, CI = 7, NW = 4, SL = T * C;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   __shared__ cx s_ex[2][T];
   __shared__ cx s_l3[NW][9];       // P, D, Nx, GL0, GR0, GL30, GR30, cAu(real), csu
@@ -62,34 +88,31 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
   const int n = P.nsteps;
   const double dt = 1.0 / n;
   const cx z1 = mk(3.0, 1.7320508075688772);
-  const double a_re = 12.0, a_im = 12.0 * 1.7320508075688772;   // 2*Re[alpha y] = 12 y_re + 12 sqrt3 y_im
+  const double a_re = 12.0, a_im = 12.0 * 1.7320508075688772;
 
   if (wid == 0) tm4_alloc(&s_tm);
   tm_fence_before();
   __syncthreads();
   tm_fence_after();
-  // this thread's lane (warp w reaches lanes 32 (w % 4) ...) and its first column
-  const uint32_t tb = s_tm + ((uint32_t)((wid & 3) * 32) << 16) + (uint32_t)((wid >> 2) * TM4_PER);
+  const uint32_t tb = s_tm + ((uint32_t)(wid * 32) << 16);
 
   for (int p = blockIdx.x; p < P.nprob; p += gridDim.x) {
     if (P.skip && P.skip[p]) continue;
     const int pp = P.pshare ? 0 : p;
     const double L = P.L[pp];
-    cx gr2;
     {
       auto wrow = [&](const Row &r, cx &wl, cx &wd, cx &wu) {   // W = z1 A + dt D
         wl = mk(fma(dt, r.Dl, z1.re * r.Al), z1.im * r.Al);
         wd = mk(fma(dt, r.Dd, z1.re * r.Ad), z1.im * r.Ad);
         wu = mk(fma(dt, r.Du, z1.re * r.Au), z1.im * r.Au);
       };
-      // ---------------------------------------------------------------- assembly + level 1 (march_irk4.cuh, UNI)
       cx ca[CI], al[CI], be[CI], gl[CI], gr[CI];
       double sAd;
       cx sl, sd, su;
       {
         Row rs = assemble_row(P, p, t * C + CI, L, dt);
-        sAd = (rs.Al != 0.0) ? rs.Al : rs.Au;   // A's row is A_off (1,4,1)
-        if (t * C + CI >= P.ni) { sl = mk(0.0); sd = mk(1.0); su = mk(0.0); }   // padding: identity row
+        sAd = (rs.Al != 0.0) ? rs.Al : rs.Au;
+        if (t * C + CI >= P.ni) { sl = mk(0.0); sd = mk(1.0); su = mk(0.0); }
         else wrow(rs, sl, sd, su);
       }
       {
@@ -122,22 +145,17 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
 #pragma unroll
         for (int k = CI - 2; k >= 0; k--) gr[k] = -(be[k] * gr[k + 1]);
       }
-      gr2 = gr[2];
-      {   // blocks A and B1 are final
-        uint32_t w32[32];
-        tm_putc(w32, 0, al[1]); tm_putc(w32, 1, al[2]); tm_putc(w32, 2, ca[0]); tm_putc(w32, 3, ca[1]); tm_putc(w32, 4, ca[2]);
-        tm_putc(w32, 5, be[0]); tm_putc(w32, 6, be[1]); tm_putc(w32, 7, sl);
-        {
-          uint32_t lo[16], hi[16];
+      {   // block A: al[1..6], ca[0..6], be[0..5], sl
+        cx blk[20];
 #pragma unroll
-          for (int i = 0; i < 16; i++) { lo[i] = w32[i]; hi[i] = w32[16 + i]; }
-          tm_st16(tb + TM4_A, lo); tm_st16(tb + TM4_A + 16, hi);
-        }
-        uint32_t w8[8];
-        tm_put(w8, 0, su.re); tm_put(w8, 1, su.im); tm_put(w8, 2, sAd); tm_put(w8, 3, 0.0);
-        tm_st8(tb + TM4_B1, w8);
+        for (int k = 0; k < 6; k++) blk[k] = al[k + 1];
+#pragma unroll
+        for (int k = 0; k < 7; k++) blk[6 + k] = ca[k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) blk[13 + k] = be[k];
+        blk[19] = sl;
+        tm_store_cx(tb + TM8_A, blk);
       }
-      // ---------------------------------------------------------------- Schur rows on the separators
       cx a, b, c;
       __syncthreads();
       s_ex[0][t] = gl[0]; s_ex[1][t] = gr[0];
@@ -148,7 +166,6 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
         b = nfma(su, gl0n, nfma(sl, gr[CI - 1], sd));
         c = -(su * gr0n);
       }
-      // ---------------------------------------------------------------- level 2: cyclic reduction
       const cx l3P = a, l3D = b, l3N = c;
       const cx A0 = (lane == 0) ? a : mk(0.0), C30 = (lane == 30) ? c : mk(0.0);
       if (lane == 31) { a = mk(0.0); b = mk(1.0); c = mk(0.0); }
@@ -180,31 +197,19 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
         return r * binv;
       };
       const cx GL = pcr(A0), GR = pcr(C30);
-      {   // blocks B2 and C
-        uint32_t w32[32], w8[8];
+      {   // block B: su, (A_off, 0), pa[0..4], pg[0..4];  block C: binv, GL, GR, gl[0..6], gr[0..6]
+        cx blk[12];
+        blk[0] = su; blk[1] = mk(sAd, 0.0);
 #pragma unroll
-        for (int s = 0; s < 5; s++) tm_putc(w32, s, pa_[s]);
+        for (int s = 0; s < 5; s++) { blk[2 + s] = pa_[s]; blk[7 + s] = pg_[s]; }
+        tm_store_cx(tb + TM8_B, blk);
+        cx blc[17];
+        blc[0] = binv; blc[1] = GL; blc[2] = GR;
 #pragma unroll
-        for (int s = 0; s < 3; s++) tm_putc(w32, 5 + s, pg_[s]);
-        {
-          uint32_t lo[16], hi[16];
-#pragma unroll
-          for (int i = 0; i < 16; i++) { lo[i] = w32[i]; hi[i] = w32[16 + i]; }
-          tm_st16(tb + TM4_B2, lo); tm_st16(tb + TM4_B2 + 16, hi);
-        }
-        tm_putc(w8, 0, pg_[3]); tm_putc(w8, 1, pg_[4]);
-        tm_st8(tb + TM4_B2 + 32, w8);
-        tm_putc(w32, 0, binv); tm_putc(w32, 1, GL); tm_putc(w32, 2, GR); tm_putc(w32, 3, gl[0]); tm_putc(w32, 4, gl[1]); tm_putc(w32, 5, gl[2]);
-        tm_putc(w32, 6, gr[0]); tm_putc(w32, 7, gr[1]);
-        {
-          uint32_t lo[16], hi[16];
-#pragma unroll
-          for (int i = 0; i < 16; i++) { lo[i] = w32[i]; hi[i] = w32[16 + i]; }
-          tm_st16(tb + TM4_C, lo); tm_st16(tb + TM4_C + 16, hi);
-        }
+        for (int k = 0; k < 7; k++) { blc[3 + k] = gl[k]; blc[10 + k] = gr[k]; }
+        tm_store_cx(tb + TM8_C, blc);
         tm_wait_st();
       }
-      // ---------------------------------------------------------------- level 3 setup
       if (lane == 31) { s_l3[wid][0] = l3P; s_l3[wid][1] = l3D; s_l3[wid][2] = l3N;
                         s_l3[wid][7] = mk((wid + 1 < NW) ? sAd : 0.0); s_l3[wid][8] = su; }
       if (lane == 0) { s_l3[wid][3] = GL; s_l3[wid][4] = GR; }
@@ -229,70 +234,66 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
         cx xn = mk(0.0);
 #pragma unroll
         for (int w = NW - 1; w >= 0; w--) { xn = nfma(cc[w], xn, dd[w]); s_minv[w][t] = xn; }
-        // the constants lane v3 needs to form R_v3, in a conflict-free table
         s_c3[t][0] = s_l3[t][0].re; s_c3[t][1] = s_l3[t][0].im; s_c3[t][2] = s_l3[t][8].re; s_c3[t][3] = s_l3[t][8].im;
         s_c3[t][4] = s_l3[t][2].re; s_c3[t][5] = s_l3[t][2].im; s_c3[t][6] = s_l3[t][7].re;
       }
       __syncthreads();
     }
     const int v3 = lane & (NW - 1);
-    // ---------------------------------------------------------------- initial condition
     double q[C], phi[C];
 #pragma unroll
     for (int k = 0; k < C; k++) { q[k] = (t * C + k < P.ni) ? 1.0 : 0.0; phi[k] = 0.0; }
     double XL = (t > 0 && t * C - 1 < P.ni) ? 1.0 : 0.0;
     double qn = ((t + 1) * C < P.ni) ? 1.0 : 0.0;
-    double *hb = P.hist + (size_t)(P.store_full ? p : blockIdx.x) * P.hist_stride + 2 * t;   // this thread's pair (k, k+1) of a slice
+    double *hb = P.hist + (size_t)(P.store_full ? p : blockIdx.x) * P.hist_stride + 2 * t;
     auto store_slice = [&](double *dst) {
-      *reinterpret_cast<double2 *>(dst) = make_double2(q[0], q[1]);
-      *reinterpret_cast<double2 *>(dst + 2 * T) = make_double2(q[2], q[3]);
+#pragma unroll
+      for (int k = 0; k < C; k += 2) *reinterpret_cast<double2 *>(dst + k * T) = make_double2(q[k], q[k + 1]);
     };
     store_slice(hb);
     const bool full = P.store_full != 0;
     const unsigned c3_v = smem_u32(&s_c3[v3][0]);
     const unsigned mw_v = smem_u32(&s_minv[wid][v3]), mm_v = smem_u32(&s_minv[(wid + NW - 1) % NW][v3]);
-
-
-    uint32_t rA[32];
-    tm_ld32(tb + TM4_A, rA);
-    tm_wait_ld();
-    tm_pin(rA);
-
-    // ---------------------------------------------------------------- the contour march
-    // PH = 0: 2j < n (store the slice), 1: 2j = n (pairs with itself), 2: 2j > n (pairs with slice n-j); one instantiation
-    // per phase keeps the selects and branches of the quadrature out of the step
     const bool l0 = (lane == 0), l30 = (lane == 30), l31 = (lane == 31);
-    double *hw = hb;                              // write cursor (slice j)
-    const double *hr = hb + (size_t)n * SL;       // read cursor (slice n-j)
+    double *hw = hb;
+    const double *hr = hb + (size_t)n * SL;
+
+    // block A as three pieces: a0 = al[1..6], ca[0], ca[1]; a1 = ca[2..6], be[0..2]; a2 = be[3..5], sl
+    uint32_t a0[32], a1[32], a2[16];
+    tm_ld32(tb + TM8_A, a0); tm_ld32(tb + TM8_A + 32, a1); tm_ld16(tb + TM8_A + 64, a2);
+    tm_wait_ld();
+    tm_pin(a0); tm_pin(a1); tm_pin(a2);
+
     auto step = [&](auto ph, const int j) {
       constexpr int PH = decltype(ph)::value;
       hw += SL; hr -= SL;
-      double2 qo01 = make_double2(0.0, 0.0), qo23 = make_double2(0.0, 0.0);
+      double2 qo[C / 2];
       if (PH == 2) {
-        qo01 = *reinterpret_cast<const double2 *>(hr);
-        qo23 = *reinterpret_cast<const double2 *>(hr + 2 * T);
+#pragma unroll
+        for (int k = 0; k < C; k += 2) qo[k / 2] = *reinterpret_cast<const double2 *>(hr + k * T);
       }
-      uint32_t rB1[8];
-      tm_ld8(tb + TM4_B1, rB1);
-      // ---- chunk solve with zero separators (block A): forward on u = y / A_off (real right-hand side), backward
+      uint32_t b0[32], b1[16];
+      tm_ld32(tb + TM8_B, b0); tm_ld16(tb + TM8_B + 32, b1);
+      // ---- chunk solve with zero separators (block A)
       cx z[CI];
       {
-        const double t0 = fma(4.0, q[0], XL + q[1]), t1 = fma(4.0, q[1], q[0] + q[2]), t2 = fma(4.0, q[2], q[1] + q[3]);
-        z[0] = mk(t0);
-        z[1] = nfma(tm_getc(rA, 0), z[0], mk(t1));
-        z[2] = nfma(tm_getc(rA, 1), z[1], mk(t2));
-        z[2] = tm_getc(rA, 4) * z[2];
-        z[1] = nfma(tm_getc(rA, 6), z[2], tm_getc(rA, 3) * z[1]);
-        z[0] = nfma(tm_getc(rA, 5), z[1], tm_getc(rA, 2) * z[0]);
+        double tk[CI];
+#pragma unroll
+        for (int k = 0; k < CI; k++) tk[k] = fma(4.0, q[k], ((k == 0) ? XL : q[k - 1]) + q[k + 1]);
+        z[0] = mk(tk[0]);
+#pragma unroll
+        for (int k = 1; k < CI; k++) z[k] = nfma(tm_getc(a0, k - 1), z[k - 1], mk(tk[k]));   // al[k]
+        auto cak = [&](int k) { return k < 2 ? tm_getc(a0, 6 + k) : tm_getc(a1, k - 2); };
+        auto bek = [&](int k) { return k < 3 ? tm_getc(a1, 5 + k) : tm_getc(a2, k - 3); };
+        z[CI - 1] = cak(CI - 1) * z[CI - 1];
+#pragma unroll
+        for (int k = CI - 2; k >= 0; k--) z[k] = nfma(bek(k), z[k + 1], cak(k) * z[k]);
       }
-      const cx sl = tm_getc(rA, 7);
-      uint32_t rB2[32], rB3[8];
-      tm_ld32(tb + TM4_B2, rB2);
-      tm_ld8(tb + TM4_B2 + 32, rB3);
+      const cx sl = tm_getc(a2, 3);
       tm_wait_ld();
-      tm_pin(rB1); tm_pin(rB2); tm_pin(rB3);
-      const cx su = mk(tm_get(rB1, 0), tm_get(rB1, 1));
-      const double sAd = tm_get(rB1, 2);
+      tm_pin(b0); tm_pin(b1);
+      const cx su = tm_getc(b0, 0);
+      const double sAd = tm_get(b0, 2);
       cx r = mk(sAd * fma(4.0, q[C - 1], q[CI - 1]));
       r = nfma(sl, z[CI - 1], r);
       const cx rsep = r;
@@ -302,26 +303,26 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
         r = nfma(su, zfn, r);
       }
       if (l31) r = mk(0.0);
-      // ---- level 2 (block B2): five cyclic-reduction stages
-#define IRK4_CR_STAGE(S, PG)                                                    \
+      uint32_t c0[32], c1[32], c2[4];
+      tm_ld32(tb + TM8_C, c0); tm_ld32(tb + TM8_C + 32, c1); tm_ld4(tb + TM8_C + 64, c2);
+      // ---- level 2: pa[s] = b cx 2+s, pg[s] = b cx 7+s  (b0 holds cx 0..7, b1 cx 8..11)
+#define IRK8_CR(S, PA, PG)                                                      \
       {                                                                             \
         cx rm = shfl_up_c(r, 1 << (S)), rp = shfl_dn_c(r, 1 << (S));                \
-        r = pfma(tm_getc(rB2, (S)), rm, pfma((PG), rp, r));                         \
+        r = pfma((PA), rm, pfma((PG), rp, r));                                      \
       }
-      IRK4_CR_STAGE(0, tm_getc(rB2, 5)) IRK4_CR_STAGE(1, tm_getc(rB2, 6)) IRK4_CR_STAGE(2, tm_getc(rB2, 7))
-      IRK4_CR_STAGE(3, tm_getc(rB3, 0)) IRK4_CR_STAGE(4, tm_getc(rB3, 1))
-#undef IRK4_CR_STAGE
-      uint32_t rC[32];
-      tm_ld32(tb + TM4_C, rC);
-      tm_ld32(tb + TM4_A, rA);      // next step's sweep coefficients
+      IRK8_CR(0, tm_getc(b0, 2), tm_getc(b0, 7)) IRK8_CR(1, tm_getc(b0, 3), tm_getc(b1, 0)) IRK8_CR(2, tm_getc(b0, 4), tm_getc(b1, 1))
+      IRK8_CR(3, tm_getc(b0, 5), tm_getc(b1, 2)) IRK8_CR(4, tm_getc(b0, 6), tm_getc(b1, 3))
+#undef IRK8_CR
       tm_wait_ld();
-      tm_pin(rC); tm_pin(rA);
-      const cx Z = r * tm_getc(rC, 0);
+      tm_pin(c0); tm_pin(c1); tm_pin(c2);
+      const cx Z = r * tm_getc(c0, 0);
       double *pb = s_pub[j & 1][wid];
       if (l0) { pb[0] = q[0]; pb[2] = z[0].re; pb[3] = z[0].im; pb[4] = Z.re; pb[5] = Z.im; }
       if (l30) { pb[6] = Z.re; pb[7] = Z.im; }
       if (l31) { pb[8] = rsep.re; pb[9] = rsep.im; }
       __syncthreads();
+      tm_ld32(tb + TM8_A, a0); tm_ld32(tb + TM8_A + 32, a1); tm_ld16(tb + TM8_A + 64, a2);   // next step's sweep coefficients
       cx Wm, Ww;
       {
         const double *pv = s_pub[j & 1][v3], *pn = s_pub[j & 1][(v3 + 1) % NW];
@@ -340,17 +341,18 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
           Wm.re += __shfl_xor_sync(0xffffffffu, Wm.re, d); Wm.im += __shfl_xor_sync(0xffffffffu, Wm.im, d);
         }
       }
-      const cx Y = l31 ? Ww : nfma(tm_getc(rC, 1), Wm, nfma(tm_getc(rC, 2), Ww, Z));   // solution at the own separator
+      const cx Y = l31 ? Ww : nfma(tm_getc(c0, 1), Wm, nfma(tm_getc(c0, 2), Ww, Z));
       cx YL = shfl_up_c(Y, 1);
-      if (l0) YL = Wm;                                                                 // previous warp's separator
-      // q+ = q - 2 Re[alpha y]
+      if (l0) YL = Wm;
+      // q+ = q - 2 Re[alpha y]: gl[k] = c cx 3+k, gr[k] = c cx 10+k  (c0 holds cx 0..7, c1 cx 8..15, c2 cx 16)
       {
-        cx y0 = nfma(tm_getc(rC, 3), YL, nfma(tm_getc(rC, 6), Y, z[0]));
-        cx y1 = nfma(tm_getc(rC, 4), YL, nfma(tm_getc(rC, 7), Y, z[1]));
-        cx y2 = nfma(tm_getc(rC, 5), YL, nfma(gr2, Y, z[2]));
-        q[0] = fma(-a_re, y0.re, fma(-a_im, y0.im, q[0]));
-        q[1] = fma(-a_re, y1.re, fma(-a_im, y1.im, q[1]));
-        q[2] = fma(-a_re, y2.re, fma(-a_im, y2.im, q[2]));
+        auto glk = [&](int k) { return k < 5 ? tm_getc(c0, 3 + k) : tm_getc(c1, k - 5); };
+        auto grk = [&](int k) { return k < 6 ? tm_getc(c1, 2 + k) : mk(tm_get(c2, 0), tm_get(c2, 1)); };
+#pragma unroll
+        for (int k = 0; k < CI; k++) {
+          const cx yk = nfma(glk(k), YL, nfma(grk(k), Y, z[k]));
+          q[k] = fma(-a_re, yk.re, fma(-a_im, yk.im, q[k]));
+        }
       }
       q[C - 1] = fma(-a_re, Y.re, fma(-a_im, Y.im, q[C - 1]));
       XL = fma(-a_re, YL.re, fma(-a_im, YL.im, XL));
@@ -359,19 +361,20 @@ __global__ void __launch_bounds__(256, 2) march_irk4_tm_kernel(MarchParams P) {
       if (PH == 0 || full) store_slice(hw);
       if (PH >= 1) {
         const double wj = __ldg(P.w + j);
-        phi[0] = fma(wj * q[0], PH == 2 ? qo01.x : q[0], phi[0]);
-        phi[1] = fma(wj * q[1], PH == 2 ? qo01.y : q[1], phi[1]);
-        phi[2] = fma(wj * q[2], PH == 2 ? qo23.x : q[2], phi[2]);
-        phi[3] = fma(wj * q[3], PH == 2 ? qo23.y : q[3], phi[3]);
+#pragma unroll
+        for (int k = 0; k < C; k += 2) {
+          phi[k] = fma(wj * q[k], PH == 2 ? qo[k / 2].x : q[k], phi[k]);
+          phi[k + 1] = fma(wj * q[k + 1], PH == 2 ? qo[k / 2].y : q[k + 1], phi[k + 1]);
+        }
       }
+      tm_wait_ld();
+      tm_pin(a0); tm_pin(a1); tm_pin(a2);
     };
     int j = 1;
-    // (two steps per loop trip, as in march_tm_kernel, spill 780 B here and are 1.5 % slower)
     for (; 2 * j < n; j++) step(std::integral_constant<int, 0>{}, j);
     if (2 * j == n) { step(std::integral_constant<int, 1>{}, j); j++; }
     for (; j <= n; j++) step(std::integral_constant<int, 2>{}, j);
 
-    // ---------------------------------------------------------------- residual, phi, Q
     double qsum = 0.0;
     const double hcell = L / (P.N - 1);
 #pragma unroll
