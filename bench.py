@@ -484,7 +484,8 @@ def main():
     # ---- the sweep to convergence, for real: every problem of this rank's block from the N=33 start field through all
     # levels to max|phi0 - phi| < 1e-9 on the target mesh; wall clock from host start fields to host result rows
     solver = scft_b200.SweepSolver(P, N0=33, levels=LEVELS, nsteps=NSTEPS, scheme=SCHEME, tol=1e-9, device=local)
-    conv = sweep.converge_block_batched(p0, p1, eta33_start(), levels=LEVELS, solver=solver)          # warm-up pass
+    conv = sweep.converge_block_batched(p0, p1, eta33_start(), levels=LEVELS, solver=solver)          # first pass (cold)
+    conv_first_s = max_over_ranks([conv["seconds"]])[0]
     barrier()
     t0 = time.perf_counter()
     conv = sweep.converge_block_batched(p0, p1, eta33_start(), levels=LEVELS, solver=solver)
@@ -548,6 +549,7 @@ def main():
                 "sweep_converged": {
                     "problems": total, "converged": int((conv_rows[:, 0] == 0).sum()), "tol": 1e-9,
                     "seconds": conv_s, "problems_per_s": total / conv_s,
+                    "seconds_first_pass": conv_first_s,   # cold: first launches of every level's kernels, per-cell free-energy weights not cached yet
                     "worst_residual": float(np.nanmax(conv_rows[:, 1])),
                     "evaluations_per_problem_mean": float(conv_rows[:, 2].mean()),
                     "evaluations_per_problem_max": float(conv_rows[:, 2].max()),
@@ -558,7 +560,7 @@ def main():
                     "rank0_seconds_start_fields": round(float(conv.get("seconds_make_sweep", 0.0)), 4),
                     "flow": "continuation N=33->65->129->257->513->1025 (drivescft.cc:291-322), preconditioned Anderson mixing on "
                             "every level, all problems of a rank in lock-step on the device; wall clock from host start fields "
-                            "to host result rows, max over ranks; no extrapolation"},
+                            "to host result rows, max over ranks, second of two passes on one solver object; no extrapolation"},
                 "parity_checked": checked * world, "max_rel_err": max_rel_all,
                 "parity": "phi, Q, residual of sampled problems vs the CPU oracle (oracle/scft_oracle.c), tolerance 1e-10",
                 "clocks": clocks,

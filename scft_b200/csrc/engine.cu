@@ -142,12 +142,25 @@ static march_fn pick(bool uni, bool odd) {
 int choose_kernel(int ni, bool uni, KernelChoice &kc, bool odd) {
   int C = 1;
   while (C < 16 && (ni + C - 1) / C > 128) C *= 2;
+  // small meshes: a contour step costs about the same ~1100 cycles per CTA whatever C is (it is the dependent chain through
+  // the three levels), so up to 8 nodes per thread and ONE warp per problem where that fits (no level 3, no barrier) multiplies
+  // the problems in flight per SM: the coarse levels of a sweep's continuation run 2-4x faster (SCFTB_NARROW_CHUNKS=1: old rule)
+  const char *narrow = getenv("SCFTB_NARROW_CHUNKS");
+  if (!(narrow && atoi(narrow))) {
+    if (ni > 32 && ni <= 64) C = 2;
+    else if (ni > 64 && ni <= 128) C = 4;
+    else if (ni > 128 && ni <= 512) C = 8;
+  }
   const char *force = getenv("SCFTB_FORCE_C");
-  if (force && atoi(force) == 4 && C == 8) C = 4;
+  if (force && atoi(force) == 4 && C == 8 && ni > 512) C = 4;
   int need = (ni + C - 1) / C;
   int T = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 256));
   if (need > 256) return 1;
   kc.fn = nullptr;
+  if (C == 2 && T == 32) kc.fn = pick<2, 32, 16>(uni, odd);
+  if (C == 4 && T == 32) kc.fn = pick<4, 32, 16>(uni, odd);
+  if (C == 8 && T == 32) kc.fn = pick<8, 32, 12>(uni, odd);
+  if (C == 8 && T == 64) kc.fn = pick<8, 64, 6>(uni, odd);
   if (C == 1 && T == 32) kc.fn = pick<1, 32, 8>(uni, odd);
   if (C == 1 && T == 64) kc.fn = pick<1, 64, 6>(uni, odd);
   if (C == 1 && T == 128) kc.fn = pick<1, 128, 4>(uni, odd);

@@ -328,7 +328,25 @@ struct scftb_pmixer {
   double tol, cap, blow;
   double *X, *G, *xbest, *xfinal, *beta, *best, *err;
   int *k_restart, *done, *iters;
+  // non-blocking progress reports for pmixer_run: after every iteration a one-block kernel counts the running problems, the
+  // count goes to pinned host memory behind an event; the host keeps PM_LOOKAHEAD iterations queued and only QUERIES events
+  static constexpr int PM_RING = 8;
+  int *d_running = nullptr;            // [PM_RING]
+  int *h_running = nullptr;            // pinned [PM_RING]
+  cudaEvent_t ev[PM_RING] = {};
 };
+
+namespace scftb {
+__global__ void pm_count_running_kernel(int nprob, const int *done, int *out) {
+  __shared__ int s[256];
+  int c = 0;
+  for (int p = threadIdx.x; p < nprob; p += 256) c += (done[p] == 0);
+  s[threadIdx.x] = c;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) { if (threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d]; __syncthreads(); }
+  if (threadIdx.x == 0) *out = s[0];
+}
+}  // namespace scftb
 
 extern "C" {
 
@@ -336,8 +354,10 @@ int scftb_pmixer_destroy(scftb_pmixer *m) {
   if (!m) return SCFTB_OK;
   cudaSetDevice(m->e->cfg.device);
   for (void *p : {(void *)m->X, (void *)m->G, (void *)m->xbest, (void *)m->xfinal, (void *)m->beta, (void *)m->best, (void *)m->err,
-                  (void *)m->k_restart, (void *)m->done, (void *)m->iters})
+                  (void *)m->k_restart, (void *)m->done, (void *)m->iters, (void *)m->d_running})
     if (p) cudaFree(p);
+  if (m->h_running) cudaFreeHost(m->h_running);
+  for (cudaEvent_t ev : m->ev) if (ev) cudaEventDestroy(ev);
   delete m;
   return SCFTB_OK;
 }
@@ -364,6 +384,9 @@ int scftb_pmixer_create(scftb_engine *e, int nprob, double tol, int nn, double c
   CKP(cudaMalloc(&m->k_restart, sizeof(int) * nprob));
   CKP(cudaMalloc(&m->done, sizeof(int) * nprob));
   CKP(cudaMalloc(&m->iters, sizeof(int) * nprob));
+  CKP(cudaMalloc(&m->d_running, sizeof(int) * scftb_pmixer::PM_RING));
+  CKP(cudaMallocHost(&m->h_running, sizeof(int) * scftb_pmixer::PM_RING));
+  for (cudaEvent_t &ev : m->ev) CKP(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CKP(cudaMemset(m->xfinal, 0, sizeof(double) * nprob * n));
   CKP(cudaMemset(m->xbest, 0, sizeof(double) * nprob * n));
   *out = m;
@@ -461,20 +484,38 @@ int scftb_pmixer_get_x(scftb_pmixer *m, void *stream, double *x, int device) {
   return SCFTB_OK;
 }
 
-// run to convergence (all problems) or maxIteration evaluations; the flags are polled from the 5th evaluation on
+// run to convergence (all problems) or maxIteration evaluations.  The host never waits for the iteration it has just issued:
+// it keeps up to PM_LOOKAHEAD iterations queued and reads the "problems still running" count of an OLDER iteration once its
+// event has fired (an iteration in which every problem is already done costs two empty launches), so a descheduled host
+// thread does not idle the GPU on the latency-bound coarse levels.
 static int pmixer_run(scftb_pmixer *m, int maxIteration, std::vector<int> &done, int *evals) {
+  constexpr int RING = scftb_pmixer::PM_RING, PM_LOOKAHEAD = 4;
   scftb_engine *e = m->e;
+  cudaStream_t st = e->stream;
   int rc = SCFTB_OK;
   bool all = false;
   done.assign(m->nprob, 0);
-  int k = 0;
+  int k = 0, checked = 0;   // iterations issued / iterations whose report has been read
   for (; !rc && k <= maxIteration && !all; k++) {
-    rc = scftb_pmixer_iterate_device(m, e->stream);
-    if (!rc && (k >= 4 || k == maxIteration)) {
-      rc = scftb_pmixer_status(m, e->stream, done.data(), nullptr, nullptr);
-      all = std::all_of(done.begin(), done.end(), [](int d) { return d != 0; });
+    rc = scftb_pmixer_iterate_device(m, st);
+    if (rc) break;
+    const int slot = k % RING;
+    pm_count_running_kernel<<<1, 256, 0, st>>>(m->nprob, m->done, m->d_running + slot);
+    g_launches++;
+    CK(cudaMemcpyAsync(m->h_running + slot, m->d_running + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(m->ev[slot], st));
+    // read every report that is ready; block only when the queue is PM_LOOKAHEAD deep (or nothing more will be issued)
+    while (checked <= k && !all) {
+      const int cs = checked % RING;
+      const bool must = (k - checked >= PM_LOOKAHEAD) || k == maxIteration;
+      cudaError_t q = must ? cudaEventSynchronize(m->ev[cs]) : cudaEventQuery(m->ev[cs]);
+      if (q == cudaErrorNotReady) break;
+      if (q != cudaSuccess) return fail(SCFTB_ERR_CUDA, std::string("pmixer_run: ") + cudaGetErrorString(q));
+      all = (m->h_running[cs] == 0);
+      checked++;
     }
   }
+  if (!rc) rc = scftb_pmixer_status(m, st, done.data(), nullptr, nullptr);   // drains the queue
   if (evals) *evals = k;
   return rc;
 }
@@ -537,6 +578,8 @@ struct scftb_sweep {
   std::vector<scftb_engine *> eng;
   std::vector<scftb_pmixer *> mix;
   double *d_a = nullptr, *d_b = nullptr;   // ping-pong field buffers [max_prob][N_target-2]
+  // free-energy weights of the target mesh per distinct (tau, L), kept across solves (they depend on nothing else)
+  std::map<std::pair<double, double>, std::pair<std::vector<double>, double>> fe_cache;
 };
 
 extern "C" {
@@ -608,16 +651,24 @@ int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double
     pcell[p] = it->second;
   }
   std::vector<double> cw((size_t)cells.size() * Nt), cf0(cells.size());
-  // started when the LAST level begins: its iterations are long kernels, so the host threads do not disturb the polling
-  // loop the way they would on the latency-bound coarse levels, and they finish well inside that level's GPU time
+  std::vector<size_t> todo;   // cells whose weights are not in the solver's cache yet
+  for (size_t c = 0; c < cells.size(); c++) {
+    auto it = s->fe_cache.find(cells[c]);
+    if (it == s->fe_cache.end()) todo.push_back(c);
+    else { std::copy(it->second.first.begin(), it->second.first.end(), &cw[c * Nt]); cf0[c] = it->second.second; }
+  }
+  // host threads under the GPU work (the iteration loop only queries events, so they do not stall it); one core is left free
   std::vector<std::thread> workers;
   auto start_workers = [&]() {
+    if (todo.empty()) return;
     const unsigned hc = std::max(2u, std::thread::hardware_concurrency());
-    const int nthr = (int)std::max(1u, std::min(std::min(16u, hc - 1), (unsigned)cells.size()));
+    const int nthr = (int)std::max(1u, std::min(std::min(16u, hc - 1), (unsigned)todo.size()));
     for (int t = 0; t < nthr; t++)
       workers.emplace_back([&, t, nthr]() {
-        for (size_t c = t; c < cells.size(); c += nthr)
+        for (size_t i = t; i < todo.size(); i += nthr) {
+          const size_t c = todo[i];
           free_energy_weights(Nt, nullptr, cells[c].first, cells[c].second, &cw[c * Nt], &cf0[c]);
+        }
       });
   };
   auto join = [&]() { for (auto &w : workers) if (w.joinable()) w.join(); };
@@ -641,7 +692,7 @@ int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double
       ce = cudaMemcpy(m->done, dead.data(), sizeof(int) * nprob, cudaMemcpyHostToDevice);
       if (ce != cudaSuccess) { rc = fail(SCFTB_ERR_CUDA, cudaGetErrorString(ce)); break; }
     }
-    if (lvl == levels - 1) start_workers();
+    if (lvl == 0) start_workers();
     rc = pmixer_run(m, s->cfg.maxit, done, nullptr);
     if (!rc) rc = scftb_pmixer_status(m, e->stream, done.data(), iters.data(), err.data());
     if (rc) break;
@@ -662,6 +713,7 @@ int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double
   }
   auto tj = std::chrono::steady_clock::now();
   join();
+  for (size_t c : todo) s->fe_cache[cells[c]] = std::make_pair(std::vector<double>(&cw[c * Nt], &cw[c * Nt] + Nt), cf0[c]);
   if (level_seconds) level_seconds[levels] = std::chrono::duration<double>(std::chrono::steady_clock::now() - tj).count();
   if (rc) return rc;
   // results on the target level: fields, Q of the last evaluation, free energy
