@@ -486,11 +486,14 @@ def main():
     solver = scft_b200.SweepSolver(P, N0=33, levels=LEVELS, nsteps=NSTEPS, scheme=SCHEME, tol=1e-9, device=local)
     conv = sweep.converge_block_batched(p0, p1, eta33_start(), levels=LEVELS, solver=solver)          # first pass (cold)
     conv_first_s = max_over_ranks([conv["seconds"]])[0]
-    barrier()
-    t0 = time.perf_counter()
-    conv = sweep.converge_block_batched(p0, p1, eta33_start(), levels=LEVELS, solver=solver)
-    torch.cuda.synchronize()
-    conv_s = max_over_ranks([time.perf_counter() - t0])[0]
+    conv_passes = []
+    for _ in range(3):   # three timed passes; the median is reported (host-side stalls of ~0.5 s hit an occasional pass on shared boxes)
+        barrier()
+        t0 = time.perf_counter()
+        conv = sweep.converge_block_batched(p0, p1, eta33_start(), levels=LEVELS, solver=solver)
+        torch.cuda.synchronize()
+        conv_passes.append(max_over_ranks([time.perf_counter() - t0])[0])
+    conv_s = float(np.median(conv_passes))
     solver.close()
     conv_rows = sweep.gather_results(conv["rows"], total, rank, world) if world > 1 else conv["rows"]
 
@@ -549,6 +552,7 @@ def main():
                 "sweep_converged": {
                     "problems": total, "converged": int((conv_rows[:, 0] == 0).sum()), "tol": 1e-9,
                     "seconds": conv_s, "problems_per_s": total / conv_s,
+                    "seconds_all_passes": [round(v, 4) for v in conv_passes],   # "seconds" is their median
                     "seconds_first_pass": conv_first_s,   # cold: first launches of every level's kernels, per-cell free-energy weights not cached yet
                     "worst_residual": float(np.nanmax(conv_rows[:, 1])),
                     "evaluations_per_problem_mean": float(conv_rows[:, 2].mean()),
@@ -560,7 +564,7 @@ def main():
                     "rank0_seconds_start_fields": round(float(conv.get("seconds_make_sweep", 0.0)), 4),
                     "flow": "continuation N=33->65->129->257->513->1025 (drivescft.cc:291-322), preconditioned Anderson mixing on "
                             "every level, all problems of a rank in lock-step on the device; wall clock from host start fields "
-                            "to host result rows, max over ranks, second of two passes on one solver object; no extrapolation"},
+                            "to host result rows, max over ranks, median of three passes after a cold one on the same solver object; no extrapolation"},
                 "parity_checked": checked * world, "max_rel_err": max_rel_all,
                 "parity": "phi, Q, residual of sampled problems vs the CPU oracle (oracle/scft_oracle.c), tolerance 1e-10",
                 "clocks": clocks,
