@@ -509,6 +509,36 @@ def main():
                 "ms_per_step": wms / args.steps, "march_kernel_ms": wmarch,
                 "hbm_frac_per_gpu": TOTAL_PROBLEMS * ni * NSTEPS * BYTES_PER_DOF_STEP / (wmarch * 1e-3) / 1e9}
 
+    # ---- extra: the same residual evaluations with the reference driver's own stepper (IRK4, scft.cc:671-693): device-resident
+    # evaluations of this rank's block, CUDA events on the launching stream, max over ranks
+    irk4 = None
+    try:
+        e4 = scft_b200.Engine(N_NODES, nsteps=NSTEPS, scheme=scft_b200.IRK4_CONSISTENT, max_batch=P, device=local)
+        taus4, Ls4, _ = sweep.make_sweep(p0, P, eta33_start())
+        for p in range(P):
+            e4.set_problem(p, taus4[p], Ls4[p])
+        d_eta4 = torch.from_numpy(make_sweep(p0, P)[2]).to(dev)
+        d_out4 = torch.empty_like(d_eta4)
+        st4 = torch.cuda.current_stream()
+        for _ in range(2):
+            e4.residual_device(P, d_eta4.data_ptr(), d_out4.data_ptr(), st4.cuda_stream)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(st4)
+        for _ in range(5):
+            e4.residual_device(P, d_eta4.data_ptr(), d_out4.data_ptr(), st4.cuda_stream)
+        ev1.record(st4)
+        barrier()
+        ms4 = max_over_ranks([ev0.elapsed_time(ev1) / 5])[0]
+        ok4 = bool(torch.isfinite(d_out4).all().item())
+        irk4 = {"kernel": e4.kernel_name(), "problems_total": total, "ms_per_evaluation_of_all_problems": ms4,
+                "dof_steps_per_s": total * ni * NSTEPS / (ms4 * 1e-3), "finite": ok4,
+                "scheme": "IRK4_CONSISTENT (2-stage Gauss-Legendre as one complex tridiagonal solve per step)"}
+        e4.close()
+        del d_eta4, d_out4
+    except Exception as exc:   # noqa: BLE001
+        irk4 = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- extra: the 2-D mesh path (configs[3], [4]); a failure here must not take the headline line down
     mesh2d = None
     if not args.no_mesh2d:
@@ -580,6 +610,10 @@ def main():
                              "bytes_per_dof_step": BYTES_PER_DOF_STEP}}
         if weak:
             line["weak"] = weak
+        if irk4:
+            if "dof_steps_per_s" in irk4:
+                irk4["hbm_frac_per_gpu"] = irk4["dof_steps_per_s"] / world * BYTES_PER_DOF_STEP / 1e9 / peak
+            line["irk4"] = irk4
         if mesh2d:
             line["mesh2d"] = mesh2d
         assert max_rel_all < 1e-10, f"GPU results differ from the oracle: {max_rel_all:.3e}"
