@@ -487,7 +487,7 @@ def main():
     conv = sweep.converge_block_batched(p0, p1, eta33_start(), levels=LEVELS, solver=solver)          # first pass (cold)
     conv_first_s = max_over_ranks([conv["seconds"]])[0]
     conv_passes = []
-    for _ in range(3):   # three timed passes; the median is reported (host-side stalls of ~0.5 s hit an occasional pass on shared boxes)
+    for _ in range(3):   # three timed passes; the median is reported
         barrier()
         t0 = time.perf_counter()
         conv = sweep.converge_block_batched(p0, p1, eta33_start(), levels=LEVELS, solver=solver)

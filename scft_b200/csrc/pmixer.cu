@@ -21,6 +21,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <thread>
 #include <vector>
@@ -578,6 +580,8 @@ struct scftb_sweep {
   std::vector<scftb_engine *> eng;
   std::vector<scftb_pmixer *> mix;
   double *d_a = nullptr, *d_b = nullptr;   // ping-pong field buffers [max_prob][N_target-2]
+  double *d_scratch = nullptr;             // Thomas scratch of the mesh transfer, sized for the largest level: a cudaMalloc /
+                                           // cudaFree pair per transfer cost up to 0.9 s of host stall in one pass out of three
   // free-energy weights of the target mesh per distinct (tau, L), kept across solves (they depend on nothing else)
   std::map<std::pair<double, double>, std::pair<std::vector<double>, double>> fe_cache;
 };
@@ -590,6 +594,7 @@ int scftb_sweep_destroy(scftb_sweep *s) {
   for (auto *e : s->eng) scftb_destroy(e);
   if (s->d_a) cudaFree(s->d_a);
   if (s->d_b) cudaFree(s->d_b);
+  if (s->d_scratch) cudaFree(s->d_scratch);
   delete s;
   return SCFTB_OK;
 }
@@ -617,7 +622,9 @@ int scftb_sweep_create(const scftb_sweep_config *cfg, int max_prob, scftb_sweep 
     s->mix.push_back(m);
   }
   const size_t words = (size_t)max_prob * (s->Ns.back() - 2);
-  if (cudaMalloc(&s->d_a, sizeof(double) * words) != cudaSuccess || cudaMalloc(&s->d_b, sizeof(double) * words) != cudaSuccess) {
+  const size_t sw = (size_t)max_prob * 3 * (s->Ns.size() > 1 ? s->Ns[s->Ns.size() - 2] - 2 : 1);
+  if (cudaMalloc(&s->d_a, sizeof(double) * words) != cudaSuccess || cudaMalloc(&s->d_b, sizeof(double) * words) != cudaSuccess ||
+      cudaMalloc(&s->d_scratch, sizeof(double) * sw) != cudaSuccess) {
     scftb_sweep_destroy(s);
     return fail(SCFTB_ERR_CUDA, "sweep: out of device memory");
   }
@@ -677,15 +684,19 @@ int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double
   cudaError_t ce = cudaMemcpy(cur, eta0, sizeof(double) * (size_t)nprob * (s->Ns[0] - 2), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) { join(); return fail(SCFTB_ERR_CUDA, std::string("sweep_solve: ") + cudaGetErrorString(ce)); }
   int lvl = 0;
+  const bool trace = getenv("SCFTB_SWEEP_TRACE") != nullptr;
+  auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
   for (; lvl < levels && !rc; lvl++) {
     auto t0 = std::chrono::steady_clock::now();
     scftb_engine *e = s->eng[lvl];
     scftb_pmixer *m = s->mix[lvl];
     for (int p = 0; p < nprob && !rc; p++) rc = scftb_set_problem(e, p, tau[p], L[p], nullptr);
     if (rc) break;
+    const double t_set = since(t0);
     m->nprob = nprob;
     rc = scftb_pmixer_reset(m, cur, 1, e->stream);
     if (rc) break;
+    const double t_reset = since(t0);
     if (lvl) {   // problems that failed on a coarser level stay out
       std::vector<int> dead(nprob);
       for (int p = 0; p < nprob; p++) dead[p] = alive[p] ? 0 : 3;
@@ -694,6 +705,7 @@ int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double
     }
     if (lvl == 0) start_workers();
     rc = pmixer_run(m, s->cfg.maxit, done, nullptr);
+    const double t_run = since(t0);
     if (!rc) rc = scftb_pmixer_status(m, e->stream, done.data(), iters.data(), err.data());
     if (rc) break;
     for (int p = 0; p < nprob; p++) {
@@ -705,11 +717,19 @@ int scftb_sweep_solve(scftb_sweep *s, int nprob, const double *tau, const double
     }
     rc = scftb_pmixer_get_x(m, e->stream, cur, 1);
     if (!rc && lvl + 1 < levels) {
-      rc = scftb_refine_uniform_batch_device(nprob, s->Ns[lvl], e->d_L, cur, nxt, e->stream);
+      refine_uniform_kernel<<<(nprob + 63) / 64, 64, 0, e->stream>>>(nprob, s->Ns[lvl], e->d_L, cur, s->Ns[lvl] - 2, s->d_scratch, nxt,
+                                                                       2 * s->Ns[lvl] - 3);
+      g_launches++;
       std::swap(cur, nxt);
-    } else if (!rc)
-      CK(cudaStreamSynchronize(e->stream));
-    if (level_seconds) level_seconds[lvl] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (!rc) {   // the next level's engine has its own stream, and the results below are copied on the default stream
+      cudaError_t se = cudaGetLastError();
+      if (se == cudaSuccess) se = cudaStreamSynchronize(e->stream);
+      if (se != cudaSuccess) rc = fail(SCFTB_ERR_CUDA, std::string("sweep_solve: ") + cudaGetErrorString(se));
+    }
+    if (level_seconds) level_seconds[lvl] = since(t0);
+    if (trace) fprintf(stderr, "sweep level %d (N=%d): set_problem %.4f reset %.4f run %.4f (%d iterations) total %.4f s\n", lvl, s->Ns[lvl], t_set,
+                       t_reset - t_set, t_run - t_reset, m->k, since(t0));
   }
   auto tj = std::chrono::steady_clock::now();
   join();
