@@ -200,7 +200,8 @@ int scftb_pmixer_iterate_device(scftb_pmixer *m, void *stream);
 int scftb_pmixer_status(scftb_pmixer *m, void *stream, int *done, int *iters, double *err);
 /* converged problems: their field; running ones: the best iterate so far.  x [nprob][N-2], host or device */
 int scftb_pmixer_get_x(scftb_pmixer *m, void *stream, double *x, int x_is_device);
-/* adm_chen-shaped convenience call for a batch: x[nprob][N-2] host in/out; returns 0 / SCFTB_ERR_NOCONV / SCFTB_ERR_NAN */
+/* adm_chen-shaped convenience call for a batch: x[nprob][N-2] host in/out; returns 0 / SCFTB_ERR_NOCONV / SCFTB_ERR_NAN.
+ * A problem that did not converge gets its BEST iterate back, with that iterate's max|phi0-phi| in err_out. */
 int scftb_padm_batch(scftb_engine *e, int nprob, double *x, double tol, int maxIteration, int nn, int *iters_out,
                      double *err_out);
 /* refine_mesh (scft.cc:132-169) for a batch of uniform meshes on the device: d_eta[nprob][N-2] -> d_eta_new[nprob][2N-3] */

@@ -532,11 +532,17 @@ int scftb_padm_batch(scftb_engine *e, int nprob, double *x, double tol, int maxI
   if (!rc) rc = pmixer_run(m, maxIteration, done, nullptr);
   if (!rc) rc = scftb_pmixer_status(m, e->stream, done.data(), iters.data(), err_out);
   if (!rc) rc = scftb_pmixer_get_x(m, e->stream, x, 0);
+  std::vector<double> best(nprob, NAN);
+  if (!rc && cudaMemcpy(best.data(), m->best, sizeof(double) * nprob, cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = fail(SCFTB_ERR_CUDA, "padm_batch: copy of the best residual norms failed");
   int status = SCFTB_OK;
   bool nanseen = false;
   for (int p = 0; p < nprob && !rc; p++) {
     if (done[p] == 2) nanseen = true;
-    if (done[p] == 0) { status = SCFTB_ERR_NOCONV; iters[p] = m->k; }
+    if (done[p] == 0) {   // not converged: x is the best iterate (scftb_pmixer_get_x), so report ITS residual norm
+      status = SCFTB_ERR_NOCONV; iters[p] = m->k;
+      if (err_out && best[p] < INFINITY) err_out[p] = best[p];
+    }
     if (iters_out) iters_out[p] = iters[p];
   }
   scftb_pmixer_destroy(m);

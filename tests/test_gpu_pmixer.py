@@ -146,3 +146,50 @@ def test_sweep_solver_to_m1024(fixtures):
         assert res < 2e-9
         assert abs(Q - rows[i, 3]) <= 1e-10 * abs(Q)
         assert abs(F - rows[i, 4]) <= 1e-9 * abs(F)
+
+
+def test_padm_edge_cases(fixtures):
+    """iteration limit -> SCFTB_ERR_NOCONV with the best iterate returned; NaN start field -> SCFTB_ERR_NAN and the other problems of
+    the batch unaffected; window 0 (plain preconditioned relaxation) still descends; non-uniform mesh (Matlab prototype's 59-node
+    adaptive mesh) converges and the oracle confirms the field"""
+    import scft_b200 as S
+    eta33 = fixtures["n33_eta"][1:-1]
+    eng = S.Engine(33, nsteps=256, scheme=S.IE_ROWSCALE, max_batch=3)
+    x0 = np.stack([eta33 * 1.05, eta33 * 0.95, eta33])
+    rc, x, iters, err = S.padm_batch(eng, x0, tol=1e-13, max_iteration=3)       # cannot converge in 4 evaluations
+    assert rc == 4 and np.all(np.isfinite(x)) and np.all(err > 1e-13)
+    res = np.abs(eng.residual(x)).max(axis=1)
+    assert np.all(res <= np.abs(eng.residual(x0)).max(axis=1))                  # the best iterate, not the last one
+    bad = x0.copy()
+    bad[1, 5] = np.nan
+    rc, x, iters, err = S.padm_batch(eng, bad, tol=1e-9, max_iteration=100)
+    assert rc == 3 and np.isnan(err[1]) and err[0] < 1e-9 and err[2] < 1e-9
+    rc, x, iters, err = S.padm_batch(eng, x0, tol=1e-30, max_iteration=5, nn=0)
+    assert rc == 4 and np.all(err <= np.abs(eng.residual(x0)).max(axis=1))
+    assert np.allclose(err, np.abs(eng.residual(x)).max(axis=1), rtol=1e-9)   # err is the norm of the returned (best) iterate
+    eng.close()
+    xs = fixtures["matlab59_x"].copy()
+    xs[-1] = max(xs[-1], xs[-2] + 1e-3)
+    em = fixtures["matlab59_eta"][1:-1]
+    eng = S.Engine(59, nsteps=256, scheme=S.IE_ROWSCALE, tau=0.5302, L=xs[-1], x=xs)
+    rc, x, iters, err = S.padm_batch(eng, em[None, :], tol=1e-9, max_iteration=300)
+    assert rc == 0 and err[0] < 1e-9, (rc, iters, err)
+    ref = O.residual(O.eta_full(xs, x[0]), O.f0_given(xs, 0.5302), scheme=O.IE_ROWSCALE, nsteps=256, L=xs[-1], x=xs)
+    assert np.abs(ref["out"]).max() < 2e-9
+    eng.close()
+
+
+def test_sweep_solver_reports_failures_without_touching_the_rest(fixtures):
+    """a problem whose start field is NaN is reported (status 2, N reached = 33) and the other problems of the batch converge"""
+    import scft_b200 as S
+    from scft_b200 import sweep
+    eta33 = fixtures["n33_eta"][1:-1]
+    taus, Ls, eta0 = sweep.make_sweep(0, 8, eta33)
+    eta0[3, :] = np.nan
+    solver = S.SweepSolver(8, N0=33, levels=3)
+    r = solver.solve(taus, Ls, eta0)
+    solver.close()
+    rows = r["rows"]
+    assert rows[3, 0] == 2 and rows[3, 6] == 33 and np.isnan(rows[3, 3])
+    ok = np.delete(np.arange(8), 3)
+    assert np.all(rows[ok, 0] == 0) and np.all(rows[ok, 1] < 1e-9) and np.all(rows[ok, 6] == 129)
