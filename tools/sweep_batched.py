@@ -50,6 +50,11 @@ def main():
               f"{full[:, 5].mean():.1f} max {full[:, 5].max():.0f}")
         print(f"  rank 0 seconds per level {np.array2string(r['level_seconds'], precision=4)}")
         print(f"  F range {np.nanmin(full[:, 4]):.6e} .. {np.nanmax(full[:, 4]):.6e}, Q range {np.nanmin(full[:, 3]):.6f} .. {np.nanmax(full[:, 3]):.6f}")
+        if total % 256 == 0 and total >= 512:   # the seeds of one (tau, L) cell must end in the same state
+            F = full[:, 4].reshape(-1, 256)
+            Qs = full[:, 3].reshape(-1, 256)
+            print(f"  seeds of a (tau, L) cell agree: max relative spread of the free energy {np.nanmax(np.ptp(F, axis=0) / np.abs(F[0])):.2e}, "
+                  f"of Q {np.nanmax(np.ptp(Qs, axis=0) / np.abs(Qs[0])):.2e} (over {F.shape[0]} seeds x 256 cells)")
         for i in np.flatnonzero(~ok)[:8]:
             print(f"  not converged: problem {i} status {int(full[i, 0])} err {full[i, 1]:.2e} reached N={int(full[i, 6])}")
     if world > 1:
