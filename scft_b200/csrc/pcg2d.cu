@@ -60,6 +60,7 @@ struct Sys2D {
 
 struct Vec2D {
   double *q, *x, *r, *z, *s, *p, *w, *b;   // z carries halos: z[-halo .. nrows+halo); others [nrows]
+  double *qp, *w1;                         // q_{j-2}, T q_{j-2}: the extrapolated initial guess of a step (step_guess)
 };
 
 struct Red2D {
@@ -223,14 +224,30 @@ __device__ __forceinline__ RowTA apply_row(const Sys2D &S, const double *__restr
   return out;
 }
 
-// start of a contour step: b = A q, initial guess x = q, r = b - T x, z = D^-1 r, p = w = 0; partial bb = b.b
-__device__ Part step_begin(const Sys2D &S, const Vec2D &V, int tid, int nthreads) {
+// Initial guess of contour step j and its residual.  Step 1 starts from x0 = q_0.  From step 2 on the guess is the linear
+// extrapolation x0 = 2 q_{j-1} - q_{j-2} along the contour (second-order instead of first-order starting error: 33 -> 22 CG
+// iterations per step at 1M DOFs), and its residual needs no second matrix application and no halo of q_{j-2}: T is linear, so
+// T x0 = 2 T q_{j-1} - T q_{j-2}, with T q_{j-1} applied here to the actual q (halos at hand) and T q_{j-2} = the value this
+// routine computed one step earlier (w1).  (Using the CG identity T q = b - r_final instead saves the application but lets the
+// drift of the recursive residual accumulate over the 2048 steps: 1.7e-9 instead of 7e-11 against the 1-D engine.)
+__device__ __forceinline__ void step_guess(const Vec2D &V, int j, int i, double q, double tq, double &x0, double &tx0) {
+  if (j == 1) { x0 = q; tx0 = tq; }
+  else { x0 = 2.0 * q - V.qp[i]; tx0 = 2.0 * tq - V.w1[i]; }
+  V.w1[i] = tq;
+}
+// bookkeeping of the extrapolation at the end of a step, before q is overwritten by x
+__device__ __forceinline__ void step_finish(const Vec2D &V, int i) { V.qp[i] = V.q[i]; }
+
+// start of a contour step: b = A q, initial guess x0 (step_guess), r = b - T x0, z = D^-1 r, p = w = 0; partial bb = b.b
+__device__ Part step_begin(const Sys2D &S, const Vec2D &V, int j, int tid, int nthreads) {
   Part acc = {0, 0, 0, 0};
   for (int i = tid; i < S.nslices * 32; i += nthreads) {
     if (i >= S.nrows) continue;
     const RowTA ta = apply_row<false, true>(S, V.q, i);   // q is stored like z (with halos), see host
-    const double bq = ta.a, r = bq - ta.t;
-    V.b[i] = bq; V.x[i] = V.q[i]; V.r[i] = r; V.z[i] = S.dinv[i] * r; V.p[i] = 0.0; V.w[i] = 0.0;
+    double x0, tx0;
+    step_guess(V, j, i, V.q[i], ta.t, x0, tx0);
+    const double bq = ta.a, r = bq - tx0;
+    V.b[i] = bq; V.x[i] = x0; V.r[i] = r; V.z[i] = S.dinv[i] * r; V.p[i] = 0.0; V.w[i] = 0.0;
     acc.d = fma(bq, bq, acc.d);
   }
   return acc;
@@ -299,6 +316,7 @@ __device__ void step_end(const March2D &M, int j, int tid, int nthreads) {
   const double wj = (2 * j >= n) ? M.wq[j] : 0.0;
   for (int i = tid; i < M.S.nrows; i += nthreads) {
     const double qv = M.V.x[i];
+    step_finish(M.V, i);
     M.V.q[i] = qv;
     if (M.store_full || 2 * j < n) M.hist[(size_t)j * M.S.nrows + i] = qv;
     if (2 * j >= n) {
@@ -323,7 +341,7 @@ __global__ void __launch_bounds__(TPB2, 4) march2d_persistent_kernel(March2D M) 
   }
   grid.sync();
   for (int j = 1; j <= M.nsteps; j++) {
-    Part pb = step_begin(S, V, tid, nthreads);
+    Part pb = step_begin(S, V, j, tid, nthreads);
     block_partials(pb, M.R.partial + ((size_t)slot * gridDim.x + blockIdx.x) * 4);
     grid.sync();
     const double bb = reduce_partials(M.R.partial + (size_t)slot * gridDim.x * 4, gridDim.x).d;
@@ -480,8 +498,10 @@ __global__ void __launch_bounds__(TPB2, 4) march2d_p2p_kernel(March2D M, P2P X, 
     for (int i = tid; i < S.nslices * 32; i += nthreads) {
       if (i >= S.nrows) continue;
       const RowTA ta = apply_row<true, true>(S, V.q, i);
-      const double bq = ta.a, r = bq - ta.t, z = S.dinv[i] * r;
-      V.b[i] = bq; V.x[i] = V.q[i]; V.r[i] = r; V.z[i] = z; V.p[i] = 0.0; V.w[i] = 0.0;
+      double x0, tx0;
+      step_guess(V, j, i, V.q[i], ta.t, x0, tx0);
+      const double bq = ta.a, r = bq - tx0, z = S.dinv[i] * r;
+      V.b[i] = bq; V.x[i] = x0; V.r[i] = r; V.z[i] = z; V.p[i] = 0.0; V.w[i] = 0.0;
       if (push_boundary(S, X, X.off_z, i, z)) __threadfence_system();
       pb.d = fma(bq, bq, pb.d);
     }
@@ -526,6 +546,7 @@ __global__ void __launch_bounds__(TPB2, 4) march2d_p2p_kernel(March2D M, P2P X, 
       const double wj = (2 * j >= n) ? M.wq[j] : 0.0;
       for (int i = tid; i < S.nrows; i += nthreads) {
         const double qv = V.x[i];
+        step_finish(V, i);
         V.q[i] = qv;
         if (push_boundary(S, X, X.off_q, i, qv)) __threadfence_system();
         if (M.store_full || 2 * j < n) M.hist[(size_t)j * S.nrows + i] = qv;
@@ -553,9 +574,9 @@ __global__ void init2d_kernel(March2D M) {
   }
   if (tid == 0) *M.iters = 0;
 }
-__global__ void __launch_bounds__(TPB2) step_begin_kernel(March2D M) {   // needs q halos; leaves bb partials
+__global__ void __launch_bounds__(TPB2) step_begin_kernel(March2D M, int j) {   // needs q halos; leaves bb partials
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  Part pb = step_begin(M.S, M.V, tid, nthreads);
+  Part pb = step_begin(M.S, M.V, j, tid, nthreads);
   block_partials(pb, M.R.partial + (size_t)blockIdx.x * 4);
 }
 __global__ void __launch_bounds__(TPB2) spmv_kernel(March2D M, int par) {   // needs z halos; leaves gamma, delta, rr partials
@@ -690,7 +711,7 @@ int scftb2d_destroy(scftb2d_engine *e) {
   if (e->comm) g_nccl.CommDestroy(e->comm);
   for (void *p : {(void *)e->M.S.col, (void *)e->M.S.valT, (void *)e->M.S.valA, (void *)e->M.S.dinv, (void *)e->d_eta,
                   (void *)e->d_peers, (void *)e->M.V.x, (void *)e->M.V.r, (void *)e->M.V.s, (void *)e->M.V.p,
-                  (void *)e->M.V.w, (void *)e->M.V.b, (void *)e->M.R.partial, (void *)e->M.R.scal, (void *)e->M.hist,
+                  (void *)e->M.V.w, (void *)e->M.V.b, (void *)e->M.V.qp, (void *)e->M.V.w1, (void *)e->M.R.partial, (void *)e->M.R.scal, (void *)e->M.hist,
                   (void *)e->M.phi, (void *)e->M.iters, (void *)e->d_out, (void *)e->d_f0, (void *)e->M.wq})
     if (p) cudaFree(p);
   cudaStreamDestroy(e->stream);
@@ -779,7 +800,7 @@ int scftb2d_create(const scftb2d_config *cfg, const char *nccl_id128, scftb2d_en
   }
   Vec2D &V = e->M.V;
   V.q = e->d_qbuf + e->halo; V.z = e->d_zbuf + e->halo;
-  for (double **p : {&V.x, &V.r, &V.s, &V.p, &V.w, &V.b}) CK2(cudaMalloc(p, sizeof(double) * nr));
+  for (double **p : {&V.x, &V.r, &V.s, &V.p, &V.w, &V.b, &V.qp, &V.w1}) CK2(cudaMalloc(p, sizeof(double) * nr));
   e->M.nsteps = n; e->M.maxit = cfg->maxit > 0 ? cfg->maxit : 100000; e->M.rtol = cfg->rtol > 0 ? cfg->rtol : 1e-12;
   e->M.store_full = cfg->store_history;
   const size_t nsl = cfg->store_history ? n + 1 : n / 2 + 1;
@@ -942,7 +963,7 @@ int scftb2d_residual(scftb2d_engine *e, const double *eta, double *out) {
     for (int j = 1; j <= M.nsteps; j++) {
       int rc = halo_exchange(e, M.V.q);
       if (rc) return rc;
-      step_begin_kernel<<<G, TPB2, 0, st>>>(M);
+      step_begin_kernel<<<G, TPB2, 0, st>>>(M, j);
       fold_partials_kernel<<<1, 32, 0, st>>>(M, G, -1);
       NK(g_nccl.AllReduce(M.R.scal, M.R.scal, 4, NCCL_DOUBLE, NCCL_SUM, e->comm, st));
       begin_finish_kernel<<<1, 32, 0, st>>>(M);
