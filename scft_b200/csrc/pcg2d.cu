@@ -42,6 +42,9 @@ namespace scftb {
 
 constexpr int SLOTS = 9;
 constexpr int TPB2 = 256;
+#ifndef MINB2D
+#define MINB2D 4   // resident blocks per SM the single-GPU persistent kernel is compiled for (register cap 64)
+#endif
 
 struct Sys2D {
   int nx, ny, nyp;          // cells, nodes per column
@@ -337,7 +340,7 @@ __device__ void step_end(const March2D &M, int j, int tid, int nthreads) {
 
 // ------------------------------------------------------------------------------------------------
 // single GPU: the whole march in one persistent cooperative kernel
-__global__ void __launch_bounds__(TPB2, 4) march2d_persistent_kernel(March2D M) {
+__global__ void __launch_bounds__(TPB2, MINB2D) march2d_persistent_kernel(March2D M) {
   cg::grid_group grid = cg::this_grid();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const Sys2D &S = M.S; const Vec2D &V = M.V;
