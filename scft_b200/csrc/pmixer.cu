@@ -37,6 +37,7 @@ constexpr int PM_NW = PM_T / 32;
 
 struct PMixParams {
   int n, N, nprob, R, nm, k;
+  int consistent;       // 1: consistent C (deal.II matrices): the inverse Jacobian also carries the inverse mass matrix
   double tol, cap, blow, sign;
   const double *F;      // [nprob][n] raw residual sign*(phi0 - phi) of X_k (engine d_out)
   const double *phi;    // [nprob][N] density of X_k (engine d_phi)
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(PM_T, 4) pmix_kernel(PMixParams A) {
   }
 
   // ---- G_k = -(F + Psi^-1 (1/2)(-Lap_h) Psi^-1 F), F = phi0 - phi
+  double *Gt = A.consistent ? Xn : Gk;   // consistent C: the model value goes to a scratch vector first (X_{k+1} is still free)
   {
     const double *ph = A.phi + (size_t)p * A.N;
     const double *xn = A.xnode ? A.xnode + (size_t)p * A.N : nullptr;
@@ -127,7 +129,25 @@ __global__ void __launch_bounds__(PM_T, 4) pmix_kernel(PMixParams A) {
         const double hl = xn[i + 1] - xn[i], hr = xn[i + 2] - xn[i + 1];
         lap = -2.0 / (hl + hr) * ((up - u) / hr - (u - um) / hl);
       }
-      Gk[i] = -(f + 0.5 * lap / psi);
+      Gt[i] = -(f + 0.5 * lap / psi);
+    }
+  }
+  if (A.consistent) {
+    // With the consistent (eta_h phi_i, phi_j) a nodal change of eta acts through the mass matrix, J_consistent = J_rowscaled (Mass/h),
+    // so the model is completed by (Mass/h)^-1 = inverse of tridiag(1,4,1)/6: entries sqrt(3) (sqrt(3)-2)^|i-j| (measured on the
+    // oracle: h^2 inv(J) mid-row -1.39, 2.20, -1.39 with decay 0.268, tests/test_preconditioner_model.py).  Applied as a
+    // 17-point convolution (0.268^8 = 3e-5; the wall corrections of the exact inverse are left to the mixing history).
+    __syncthreads();
+    const double rho = 1.7320508075688772 - 2.0, s3 = 1.7320508075688772;
+    for (int i = tid; i < n; i += PM_T) {
+      double acc = Gt[i], wgt = 1.0;
+#pragma unroll
+      for (int d = 1; d <= 8; d++) {
+        wgt *= rho;
+        const double a = (i - d >= 0) ? Gt[i - d] : 0.0, b = (i + d < n) ? Gt[i + d] : 0.0;
+        acc = fma(wgt, a + b, acc);
+      }
+      Gk[i] = s3 * acc;
     }
   }
   __syncthreads();   // G_k visible to the whole CTA
@@ -432,6 +452,7 @@ int scftb_pmixer_iterate_device(scftb_pmixer *m, void *stream) {
   PMixParams A;
   A.n = e->ni; A.N = e->cfg.N; A.nprob = m->nprob; A.R = m->R; A.nm = m->nm; A.k = m->k;
   A.tol = m->tol; A.cap = m->cap; A.blow = m->blow; A.sign = e->cfg.sign;
+  A.consistent = (e->cfg.scheme != SCFTB_IE_ROWSCALE && !getenv("SCFTB_PMIX_NO_MASS")) ? 1 : 0;
   A.F = e->d_out; A.phi = e->d_phi; A.L = e->d_L; A.xnode = e->uniform ? nullptr : e->d_x;
   A.X = m->X; A.G = m->G; A.xbest = m->xbest; A.xfinal = m->xfinal;
   A.beta = m->beta; A.best = m->best; A.err = m->err;

@@ -193,3 +193,17 @@ def test_sweep_solver_reports_failures_without_touching_the_rest(fixtures):
     assert rows[3, 0] == 2 and rows[3, 6] == 33 and np.isnan(rows[3, 3])
     ok = np.delete(np.arange(8), 3)
     assert np.all(rows[ok, 0] == 0) and np.all(rows[ok, 1] < 1e-9) and np.all(rows[ok, 6] == 129)
+
+
+def test_sweep_solver_consistent_scheme(fixtures):
+    """IE on the deal.II matrices (consistent C): the preconditioner carries the inverse mass matrix as well; 32 problems through
+    four levels, every problem within 20 evaluations on the target mesh, the oracle confirms a field"""
+    import scft_b200 as S
+    from scft_b200 import sweep
+    eta33 = fixtures["n33_eta"][1:-1]
+    r = sweep.converge_block_batched(0, 32, eta33, levels=4, scheme=S.IE_CONSISTENT, want_fields=True)
+    rows = r["rows"]
+    assert np.all(rows[:, 0] == 0) and np.all(rows[:, 1] < 1e-9) and rows[:, 5].max() <= 20, rows[:, [0, 1, 5]]
+    tau, L, _ = sweep.sweep_params(7)
+    res, Q, F = _oracle_check(257, tau, L, r["eta"][7], scheme=O.IE_CONSISTENT)
+    assert res < 2e-9 and abs(Q - rows[7, 3]) <= 1e-10 * abs(Q) and abs(F - rows[7, 4]) <= 1e-9 * abs(F)

@@ -47,16 +47,22 @@ def test_inverse_jacobian_is_tridiagonal_and_matches_the_model(oracle, fixtures)
 def test_model_clusters_the_spectrum_for_the_consistent_schemes(oracle, fixtures):
     """deal.II matrices (consistent C: implicit Euler and the reference's IRK4): inv(J) carries the inverse mass matrix as well
     (off-diagonals decay by 0.27 per node instead of vanishing), but the same local model still collapses the spectrum of J from
-    2.9 decades to less than one — which is all the mixing history needs"""
+    2.9 decades to less than one, and completed by the inverse mass matrix (J_consistent = J_rowscaled Mass/h) to half a decade"""
     x = fixtures["n33_x"]
     em = fixtures["n33_eta"][1:-1].copy()
     f0 = oracle.f0_given(x)
     n, h = len(em), x[1] - x[0]
     lap = (2 * np.eye(n) - np.eye(n, k=1) - np.eye(n, k=-1)) / (h * h)
+    rho = np.sqrt(3.0) - 2.0      # the 17-point convolution pmix_kernel applies for (Mass/h)^-1 = inverse of tridiag(1,4,1)/6
+    conv = np.sqrt(3.0) * sum((rho ** abs(d)) * np.eye(n, k=d) for d in range(-8, 9))
     for scheme in (oracle.IE_CONSISTENT, oracle.IRK4_CONSISTENT):
         J, F0 = _jacobian(oracle, x, f0, em, scheme, 512)
         w = np.linalg.eigvalsh(0.5 * (J + J.T))
         assert w.max() / w.min() > 500
         psi = np.sqrt(F0["phi"][1:-1])
-        ev = np.linalg.eigvals((np.eye(n) + 0.5 * lap / np.outer(psi, psi)) @ J).real
+        M = np.eye(n) + 0.5 * lap / np.outer(psi, psi)
+        ev = np.linalg.eigvals(M @ J).real
         assert ev.min() > 0.3 and ev.max() < 3.0
+        # with the mass-matrix factor the spectrum is the row-scaled scheme's: [1.0, 2.9]
+        ev = np.linalg.eigvals(conv @ M @ J).real
+        assert ev.min() > 0.95 and ev.max() < 3.2
