@@ -102,3 +102,20 @@ def test_dealii_flow_preconditioned_mixing_to_m1024(sb, oracle, fixtures, tmp_pa
     ref = oracle.residual(oracle.eta_full(x, eta[1:-1]), oracle.f0_given(x), scheme=oracle.IE_ROWSCALE, nsteps=2048)
     assert np.abs(ref["out"]).max() < 2e-9       # the file keeps 15 decimals of eta
     assert rows[-1]["F"] == pytest.approx(0.001909977319, abs=2e-11)   # device Broyden's value, profiles/r1_continuation_m1024.txt
+
+
+def test_dealii_flow_irk4_with_preconditioned_mixing(sb, oracle, fixtures, tmp_path):
+    """the reference driver's own configuration (IRK4, drivescft.cc:130-146) with the preconditioned mixer instead of broydn: from
+    the reference's converged N=33 file through three refinement levels; level 0 keeps the file's free energy, every saved file
+    re-evaluates on the oracle"""
+    inp = str(tmp_path / "N=33_for_read.txt")
+    sb.write_solution(inp, float(fixtures["n33_error"]), float(fixtures["n33_F"]), fixtures["n33_x"], fixtures["n33_eta"])
+    rows = run_driver([inp, "--flow", "dealii", "--scheme", "irk4", "--solver", "padm", "--levels", "3", "--tol", "1e-10",
+                       "--outdir", str(tmp_path)])
+    assert [r["N"] for r in rows] == [33, 65, 129] and all(r["check"] == 0 and r["err"] < 1e-10 for r in rows)
+    assert rows[0]["F"] == pytest.approx(float(fixtures["n33_F"]), rel=2e-8)     # the file itself is converged to 1.4e-9 only
+    for r in rows:
+        x, eta = sb.read_solution(str(tmp_path / f"solution_yita_1D_N={r['N']:03d}.txt"))
+        ref = oracle.residual(oracle.eta_full(x, eta[1:-1]), oracle.f0_given(x), scheme=oracle.IRK4_CONSISTENT, nsteps=2048)
+        assert np.abs(ref["out"]).max() < 5e-10
+        assert oracle.free_energy(x, oracle.eta_full(x, eta[1:-1])) == pytest.approx(r["F"], abs=1e-11)
